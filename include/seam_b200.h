@@ -1,0 +1,151 @@
+/* seam_b200.h -- C ABI of the B200-native SEAM Match-RCNN retrieval hot path.
+ *
+ * The reference (HumaticsLAB/SEAM-Match-RCNN) is pure Python and has no FFI; the boundary
+ * it offers is its nn.Module surface and the evaluation scripts' score / rank outputs.
+ * Each entry point below names the reference code it replaces (paths relative to the
+ * reference root).  The Python host package binds these with ctypes and keeps the
+ * reference's module signatures on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors' data_ptr());
+ *     the library never allocates or frees caller-visible memory.  The handle owns only the
+ *     folded weights.
+ *   - all calls enqueue work on `stream` (a cudaStream_t passed as void*) and return
+ *     without synchronising the host.
+ *   - return value: 0 = OK, otherwise a seam_status; text via seam_last_error().
+ *   - no CPU fallback exists: without a CUDA device every compute call fails.
+ *   - D = 256 channels (models/match_head.py:81), inter channels 128 (models/nlb.py:15-17).
+ */
+#ifndef SEAM_B200_H_
+#define SEAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct seam_handle seam_handle;
+
+enum seam_status {
+  SEAM_OK = 0,
+  SEAM_ERR_BAD_ARG = 1,      /* null pointer, negative size, misaligned pointer */
+  SEAM_ERR_UNSUPPORTED = 2,  /* outside the envelope: T > 64, k > 32, strides not 16-byte multiples */
+  SEAM_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed */
+  SEAM_ERR_STATE = 4,        /* weights not loaded, workspace too small */
+};
+
+enum { SEAM_D = 256, SEAM_DI = 128, SEAM_MAX_T = 64, SEAM_MAX_K = 32 };
+
+/* ABI version of this header (bumped on any signature change). */
+int seam_abi_version(void);
+
+/* One handle per device.  Not thread-safe; distinct handles are independent. */
+int seam_create(seam_handle** out, int device);
+void seam_destroy(seam_handle* h);
+const char* seam_last_error(const seam_handle* h);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+uint64_t seam_launch_count(const seam_handle* h);
+
+/* Hot-path weights, fp32, device pointers, in the reference's state_dict layout
+ * (TemporalAggregationNLB().state_dict()):
+ *   newnlb.{theta,phi,g}.weight (128,256,1) / .bias (128)      models/nlb.py:34,51,54
+ *   newnlb.W.weight (256,128,1) / .bias (256)                  models/nlb.py:45-49
+ *   newnlb.concat_project.0.weight (1,256,1,1)                 models/nlb.py:57-60
+ *   attention_scorer.weight (1,256) / .bias (1)                models/match_head.py:86
+ *   last.weight (2,256) / .bias (2)                            models/match_head.py:64   */
+typedef struct seam_weights {
+  const float* theta_w; const float* theta_b;
+  const float* phi_w;   const float* phi_b;
+  const float* g_w;     const float* g_b;
+  const float* W_w;     const float* W_b;
+  const float* concat_w;
+  const float* att_w;   const float* att_b;
+  const float* last_w;  const float* last_b;
+} seam_weights;
+
+/* Folds the weights on the device into the collapsed form the kernels use (DESIGN.md "K1
+ * algebra").  Replaces nothing at run time in the reference -- it is what
+ * nn.Module.load_state_dict (evaluate_movingfashion.py:502-503) becomes. */
+int seam_load_weights(seam_handle* h, const seam_weights* w, void* stream);
+
+/* Only `last` (match_predictor.last, models/match_head.py:64): enough for the scorer entry
+ * points when no aggregation is needed (per-frame scorers, evaluate_movingfashion.py:94-121). */
+int seam_load_scorer(seam_handle* h, const float* last_w, const float* last_b, void* stream);
+
+/* ---- (a) temporal aggregation ------------------------------------------------------
+ * Replaces the seq-branch of TemporalAggregationNLB.forward, models/match_head.py:133-154:
+ * per-track unpack (first True of the mask row ends the track, row 0 is a dummy),
+ * NONLocalBlock1D when T_i > 1 (models/nlb.py:66-101), attention_scorer + softmax over
+ * frames + weighted sum.
+ *   seq          (1+Tmax, Q, 256) fp32 addressed as seq[t*frame_stride + i*track_stride + c]
+ *                (strides in floats, multiples of 4; the reference layout is
+ *                frame_stride = Q*256, track_stride = 256)
+ *   mask         (Q, 1+Tmax) uint8 (torch.bool), nonzero = padding; may be NULL
+ *   lens         (Q) int32 frames per track (overrides mask when non-NULL); may be NULL;
+ *                both NULL means every track has Tmax frames
+ *   out          (Q, 256) fp32  = x3_1b
+ *   att          (Q, Tmax) fp32 attention weights p (zero beyond T_i), or NULL  (getatt=True)
+ *   workspace    seam_aggregate_workspace_bytes(Q) bytes, 256-byte aligned              */
+size_t seam_aggregate_workspace_bytes(int Q);
+int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const int32_t* lens, int Tmax, int Q,
+                   int64_t frame_stride, int64_t track_stride, float* out, float* att, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Full non-local block output (not pooled): NONLocalBlock1D.forward, models/nlb.py:66-101.
+ *   x, z  (B, 256, T) fp32 channel-major as in the reference; T <= 64.
+ *   workspace  seam_nlb_workspace_bytes(B, T) bytes                                        */
+size_t seam_nlb_workspace_bytes(int B, int T);
+int seam_nlb_forward(seam_handle* h, const float* x, int B, int T, float* z, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---- (b)+(c) pair scorer and per-query top-k ----------------------------------------
+ * Gallery preparation (once per gallery shard): fp16 copy for the tensor-core pass, the
+ * per-item term cg_j = sum_k dw_k g_jk^2 (dw = last.weight[1]-last.weight[0]) and
+ * gstat[0] = max_j ||g_j||_2.  g (G,256) fp32 -> g16 (G,256) fp16, cg (G) fp32, gstat (4) fp32. */
+int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float* cg, float* gstat, void* stream);
+
+/* Fused scorer + top-k.  Replaces, for all queries at once, the per-query loop body
+ * evaluate_movingfashion.py:263-269 (evaluate_multiDF2.py:220-226):
+ *   sq_diffs = (gallery - q)**2 ; raw = sq_diffs @ W.T + b ; softmax[...,1] ; argsort desc
+ * and the module tail models/match_head.py:160-162 without materialising x4 / x5.
+ *   q (Q,256) fp32 queries; g (G,256) fp32 gallery shard with its prepared g16 / cg / gstat
+ *   out_score  (Q,k) fp32  softmax(x5)[...,1] of the k best, best first
+ *   out_margin (Q,k) fp32  l1 - l0 of the same entries (ranking key; does not saturate)
+ *   out_idx    (Q,k) int32 gallery row + index_offset, -1 where G < k
+ * Ordering: margin descending, ties by lowest index.  Results are those of the fp32
+ * direct form; the fp16 tensor-core pass only nominates candidates, every returned entry is
+ * re-scored in fp32 and rows whose candidate set cannot be proven complete are re-ranked
+ * exhaustively (DESIGN.md "certified top-k").  k <= SEAM_MAX_K.
+ *   stats      optional (4) int32: [0] = rows that took the exhaustive path               */
+size_t seam_score_workspace_bytes(const seam_handle* h, int Q, int G, int k);
+/* Introspection: how seam_score_topk decomposes a (Q,G) problem and lays out its workspace.
+ * out[0] query tiles (128 rows), [1] gallery tiles (256 rows), [2] parts P per query tile,
+ * [3] gallery tiles per part, [4] work items, [5..12] byte offsets of {a16, rq, anorm,
+ * thr, cand_v, cand_i, counters, fallback_rows} in the workspace, [13] workspace bytes. */
+int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out14);
+int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const void* g16, const float* cg,
+                    const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin,
+                    int32_t* out_idx, int32_t* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dense logits (parity / small problems): x5 (Q,G,2) fp32 = last((q-g)^2).
+ * models/match_head.py:160-162 and MatchPredictor.forward :70-74. */
+int seam_score_dense(seam_handle* h, const float* q, int Q, const float* g, int G, float* x5, void* stream);
+
+/* Rank of one designated gallery item per query (0 = best), the quantity the eval script
+ * reads out of its full argsort: evaluate_movingfashion.py:268-269.
+ *   target (Q) int32 gallery row;  out_rank (Q) int32;  out_margin (Q) fp32 optional   */
+int seam_rank_of_target(seam_handle* h, const float* q, int Q, const float* g, int G, const int32_t* target,
+                        int32_t* out_rank, float* out_margin, void* stream);
+
+/* Merge N per-shard top-k lists (after the all-gather) into one: lists are (N,Q,k)
+ * contiguous; entries with idx < 0 are invalid.  Same ordering contract as seam_score_topk.
+ * No reference counterpart (the reference ranks a single gallery). */
+int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, const int32_t* idx, int N, int Q,
+                    int k, float* out_score, float* out_margin, int32_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEAM_B200_H_ */

@@ -1,0 +1,438 @@
+// Scorer support kernels: operand preparation for the tensor-core pass, fp32 direct-form
+// re-scoring + certification of the nominated candidates, the exhaustive fp32 ranking used
+// for rows that cannot be certified, dense logits, rank-of-target and the shard merge.
+//
+// "Direct form" below always means the reference's own arithmetic, in fp32:
+//   l_c = sum_k W[c][k] * (q_k - g_k)^2 + b_c   (models/match_head.py:161-162,
+//   evaluate_movingfashion.py:263-264), score = softmax(l)[1] (:265-267).
+#pragma once
+#include <climits>
+#include <cstdint>
+#include <cuda_fp16.h>
+#include "fold.cuh"
+#include "sm100_ptx.cuh"
+#include "warp_sort.cuh"
+
+namespace seam {
+namespace exact {
+
+constexpr float FP16_MAX = 65504.f;
+// bound on |fp16 tensor-core value - exact value| relative to ||a_i|| * max_j ||g_j||:
+// two operand roundings (2^-11 each) + fp32 accumulation slack.
+constexpr float EPS_COEFF = 9.9e-4f;   // 2^-10 = 9.77e-4, plus accumulation slack
+
+__device__ __forceinline__ float softmax1(float l0, float l1) {
+  const float m = fmaxf(l0, l1);
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+  return e1 / (e0 + e1);
+}
+
+// this lane's slice of a 256-vector: elements [4l,4l+4) and [128+4l,128+4l+4)
+struct Slice {
+  float4 lo, hi;
+};
+__device__ __forceinline__ Slice load_slice(const float* row, int lane) {
+  Slice s;
+  s.lo = *reinterpret_cast<const float4*>(row + 4 * lane);
+  s.hi = *reinterpret_cast<const float4*>(row + 128 + 4 * lane);
+  return s;
+}
+__device__ __forceinline__ void sqdiff_dot2(const Slice& q, const Slice& g, const Slice& w0, const Slice& w1,
+                                            float& p0, float& p1) {
+  float d, s;
+  p0 = 0.f;
+  p1 = 0.f;
+#define SEAM_TERM(F)        \
+  d = q.F - g.F;            \
+  s = d * d;                \
+  p0 = fmaf(w0.F, s, p0);   \
+  p1 = fmaf(w1.F, s, p1);
+  SEAM_TERM(lo.x) SEAM_TERM(lo.y) SEAM_TERM(lo.z) SEAM_TERM(lo.w)
+  SEAM_TERM(hi.x) SEAM_TERM(hi.y) SEAM_TERM(hi.z) SEAM_TERM(hi.w)
+#undef SEAM_TERM
+}
+// both logits of one pair, all lanes get the result
+__device__ __forceinline__ void pair_logits(const Slice& q, const float* grow, const Slice& w0, const Slice& w1,
+                                            float b0, float b1, int lane, float& l0, float& l1) {
+  const Slice g = load_slice(grow, lane);
+  float p0, p1;
+  sqdiff_dot2(q, g, w0, w1, p0, p1);
+  l0 = ptx::warp_sum(p0) + b0;
+  l1 = ptx::warp_sum(p1) + b1;
+}
+
+// ---------------------------------------------------------------- gallery preparation
+// warp per gallery row: fp16 copy, cg_j = dw . g_j^2, max_j ||g_j|| (gstat[0]), overflow flag (gstat[1])
+__global__ void __launch_bounds__(256) prep_gallery_kernel(const float* __restrict__ g, int G,
+                                                           const float* __restrict__ fold, __half* __restrict__ g16,
+                                                           float* __restrict__ cg, float* __restrict__ gstat) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= G) return;
+  const Slice x = load_slice(g + (size_t)j * 256, lane);
+  const Slice dw = load_slice(fold + Fold::DW, lane);
+  const float xs[8] = {x.lo.x, x.lo.y, x.lo.z, x.lo.w, x.hi.x, x.hi.y, x.hi.z, x.hi.w};
+  const float ds[8] = {dw.lo.x, dw.lo.y, dw.lo.z, dw.lo.w, dw.hi.x, dw.hi.y, dw.hi.z, dw.hi.w};
+  float c = 0.f, n2 = 0.f, amax = 0.f;
+  __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    c = fmaf(ds[e], xs[e] * xs[e], c);
+    n2 = fmaf(xs[e], xs[e], n2);
+    amax = fmaxf(amax, fabsf(xs[e]));
+    h[e] = __float2half_rn(xs[e]);
+  }
+  __half* dst = g16 + (size_t)j * 256;
+  *reinterpret_cast<uint2*>(dst + 4 * lane) = *reinterpret_cast<const uint2*>(&h[0]);
+  *reinterpret_cast<uint2*>(dst + 128 + 4 * lane) = *reinterpret_cast<const uint2*>(&h[4]);
+  c = ptx::warp_sum(c);
+  n2 = ptx::warp_sum(n2);
+  amax = ptx::warp_max(amax);
+  if (lane == 0) {
+    cg[j] = c;
+    atomicMax(reinterpret_cast<unsigned int*>(gstat), __float_as_uint(sqrtf(n2)));   // non-negative floats
+    if (!(amax < FP16_MAX)) atomicMax(reinterpret_cast<unsigned int*>(gstat + 1), __float_as_uint(1.f));
+  }
+}
+
+// ---------------------------------------------------------------- query preparation
+// warp per query: a = -2 dw (.) q as fp16, rq = dw . q^2, ||a||, threshold reset
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int Q,
+                                                           const float* __restrict__ fold, __half* __restrict__ a16,
+                                                           float* __restrict__ rq, float* __restrict__ anorm,
+                                                           uint32_t* __restrict__ thr_global,
+                                                           int32_t* __restrict__ counters) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counters[0] = 0;   // rows needing the exhaustive pass
+    counters[1] = 0;   // fp16 overflow among the queries
+  }
+  if (i >= Q) return;
+  const Slice x = load_slice(q + (size_t)i * 256, lane);
+  const Slice dw = load_slice(fold + Fold::DW, lane);
+  const float xs[8] = {x.lo.x, x.lo.y, x.lo.z, x.lo.w, x.hi.x, x.hi.y, x.hi.z, x.hi.w};
+  const float ds[8] = {dw.lo.x, dw.lo.y, dw.lo.z, dw.lo.w, dw.hi.x, dw.hi.y, dw.hi.z, dw.hi.w};
+  float r = 0.f, n2 = 0.f, amax = 0.f;
+  __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float a = -2.f * ds[e] * xs[e];
+    r = fmaf(ds[e], xs[e] * xs[e], r);
+    n2 = fmaf(a, a, n2);
+    amax = fmaxf(amax, fabsf(a));
+    h[e] = __float2half_rn(a);
+  }
+  __half* dst = a16 + (size_t)i * 256;
+  *reinterpret_cast<uint2*>(dst + 4 * lane) = *reinterpret_cast<const uint2*>(&h[0]);
+  *reinterpret_cast<uint2*>(dst + 128 + 4 * lane) = *reinterpret_cast<const uint2*>(&h[4]);
+  r = ptx::warp_sum(r);
+  n2 = ptx::warp_sum(n2);
+  amax = ptx::warp_max(amax);
+  if (lane == 0) {
+    rq[i] = r;
+    anorm[i] = sqrtf(n2);
+    thr_global[i] = ptx::float_to_ordered(-INFINITY);
+    if (!(amax < FP16_MAX)) atomicExch(counters + 1, 1);
+  }
+}
+
+// ---------------------------------------------------------------- re-score + certify
+struct RescoreParams {
+  const float* q;        // (Q,256)
+  const float* g;        // (G,256)
+  const float* fold;
+  const float* cand_v;   // (Q,P,32)
+  const int32_t* cand_i;
+  const float* rq;
+  const float* anorm;
+  const float* gstat;
+  int Q, G, P, k, index_offset;
+  float* out_score;
+  float* out_margin;
+  int32_t* out_idx;
+  int32_t* counters;      // [0] number of uncertified rows, [1] query overflow flag
+  int32_t* fallback_rows; // (Q)
+};
+
+// warp per query.  Merges the per-part candidate lists to the best 32 by approximate value,
+// re-scores them in the fp32 direct form, orders them (margin desc, index asc), writes the
+// first k, and decides whether the result is provably the exact top-k:
+//   every item NOT among the 32 has approximate value <= tau (the 32nd approximate value),
+//   hence exact margin <= tau + rq + db + eps;  the list is exact if margin_k exceeds that.
+__global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= p.Q) return;
+  float cv;
+  uint32_t cidx;
+  {
+    const size_t o = (size_t)qi * p.P * 32;
+    cv = p.cand_v[o + lane];
+    cidx = (uint32_t)p.cand_i[o + lane];
+    for (int part = 1; part < p.P; ++part) {
+      const float nv = p.cand_v[o + part * 32 + (31 - lane)];
+      const uint32_t ni = (uint32_t)p.cand_i[o + part * 32 + (31 - lane)];
+      if (nv > cv) {
+        cv = nv;
+        cidx = ni;
+      }
+      wsort::merge32<true>(cv, cidx, lane);
+    }
+  }
+  const float tau = __shfl_sync(ptx::FULL_MASK, cv, 31);
+  const Slice qs = load_slice(p.q + (size_t)qi * 256, lane);
+  const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
+  const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
+  const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
+  float my_l0 = 0.f, my_l1 = 0.f;
+  for (int c = 0; c < 32; ++c) {
+    const int idx = __shfl_sync(ptx::FULL_MASK, (int)cidx, c);
+    if (idx < 0) continue;   // warp-uniform
+    float l0, l1;
+    pair_logits(qs, p.g + (size_t)idx * 256, w0, w1, b0, b1, lane, l0, l1);
+    if (lane == c) {
+      my_l0 = l0;
+      my_l1 = l1;
+    }
+  }
+  const bool valid = (int)cidx >= 0;
+  float d = valid ? my_l1 - my_l0 : -INFINITY;
+  int id = valid ? (int)cidx : INT_MAX;
+  float sc = valid ? softmax1(my_l0, my_l1) : 0.f;
+  wsort::sort32_rank(d, id, sc, lane);
+  if (lane < p.k) {
+    const size_t o = (size_t)qi * p.k + lane;
+    const bool ok = id != INT_MAX;
+    p.out_score[o] = sc;
+    p.out_margin[o] = d;
+    p.out_idx[o] = ok ? id + p.index_offset : -1;
+  }
+  const float dk = __shfl_sync(ptx::FULL_MASK, d, p.k - 1);
+  if (lane == 0) {
+    bool certified;
+    if (p.G <= 32) {
+      certified = true;                       // every item was a candidate
+    } else {
+      const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
+      const float db = p.fold[Fold::CONSTS + 4];
+      const float eps = EPS_COEFF * p.anorm[qi] * p.gstat[0] + 2e-5f * (1.f + fabsf(dk));
+      certified = !overflow && (dk >= tau + p.rq[qi] + db + eps);
+    }
+    if (!certified) {
+      const int slot = atomicAdd(p.counters, 1);
+      p.fallback_rows[slot] = qi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- exhaustive fp32 ranking
+struct ExactParams {
+  const float* q;
+  const float* g;
+  const float* fold;
+  int Q, G, k, index_offset;
+  const int32_t* count;   // number of rows to process (device), or null: all Q rows
+  const int32_t* rows;    // row list when count != null
+  float* out_score;
+  float* out_margin;
+  int32_t* out_idx;
+};
+
+// CTA (8 warps) per row: each warp scans every 8th gallery item keeping a sorted best-32 in
+// its lanes, the eight lists are merged through shared memory.
+__global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
+  __shared__ float sd[8][32];
+  __shared__ int si[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nrows = p.count ? *p.count : p.Q;
+  const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
+  const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
+  const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
+  for (int e = blockIdx.x; e < nrows; e += gridDim.x) {
+    const int qi = p.count ? p.rows[e] : e;
+    const Slice qs = load_slice(p.q + (size_t)qi * 256, lane);
+    float cd = -INFINITY;
+    int cidx = INT_MAX;
+    for (int j = warp; j < p.G; j += 8) {
+      float l0, l1;
+      pair_logits(qs, p.g + (size_t)j * 256, w0, w1, b0, b1, lane, l0, l1);
+      const float d = l1 - l0;
+      const float wd = __shfl_sync(ptx::FULL_MASK, cd, 31);
+      const int wi = __shfl_sync(ptx::FULL_MASK, cidx, 31);
+      if (wsort::ranks_before(d, j, wd, wi)) {   // warp-uniform
+        const int pos = __popc(__ballot_sync(ptx::FULL_MASK, wsort::ranks_before(cd, cidx, d, j)));
+        const float ud = __shfl_up_sync(ptx::FULL_MASK, cd, 1);
+        const int ui = __shfl_up_sync(ptx::FULL_MASK, cidx, 1);
+        if (lane > pos) {
+          cd = ud;
+          cidx = ui;
+        } else if (lane == pos) {
+          cd = d;
+          cidx = j;
+        }
+      }
+    }
+    sd[warp][lane] = cd;
+    si[warp][lane] = cidx;
+    __syncthreads();
+    if (warp == 0) {
+      float dummy = 0.f;
+      for (int w = 1; w < 8; ++w) {
+        const float od = sd[w][31 - lane];
+        const int oi = si[w][31 - lane];
+        if (wsort::ranks_before(od, oi, cd, cidx)) {
+          cd = od;
+          cidx = oi;
+        }
+        wsort::merge32_rank(cd, cidx, dummy, lane);
+      }
+      // scores of the winners
+      float my_sc = 0.f;
+      for (int c = 0; c < p.k; ++c) {
+        const int idx = __shfl_sync(ptx::FULL_MASK, cidx, c);
+        if (idx == INT_MAX) continue;
+        float l0, l1;
+        pair_logits(qs, p.g + (size_t)idx * 256, w0, w1, b0, b1, lane, l0, l1);
+        if (lane == c) my_sc = softmax1(l0, l1);
+      }
+      if (lane < p.k) {
+        const size_t o = (size_t)qi * p.k + lane;
+        const bool ok = cidx != INT_MAX;
+        p.out_score[o] = ok ? my_sc : 0.f;
+        p.out_margin[o] = cd;
+        p.out_idx[o] = ok ? cidx + p.index_offset : -1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- dense logits
+// x5 (Q,G,2).  32 queries x 32 gallery rows per CTA, operands staged in shared memory.
+__global__ void __launch_bounds__(256) dense_logits_kernel(const float* __restrict__ q, int Q,
+                                                           const float* __restrict__ g, int G,
+                                                           const float* __restrict__ fold, float* __restrict__ x5) {
+  __shared__ float qs[32][129];
+  __shared__ float gs[32][129];
+  __shared__ float ws[2][256];
+  const int t = threadIdx.x;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  ws[0][t] = fold[Fold::LAST_W + t];
+  ws[1][t] = fold[Fold::LAST_W + 256 + t];
+  const int tx = t & 31, ty = t >> 5;   // gallery row, query group (4 queries each)
+  float l0[4] = {}, l1[4] = {};
+  for (int kh = 0; kh < 256; kh += 128) {   // K staged in two halves (static smem <= 48 KB)
+    __syncthreads();
+    for (int e = t; e < 32 * 128; e += 256) {
+      const int r = e >> 7, c = e & 127;
+      qs[r][c] = (i0 + r < Q) ? q[(size_t)(i0 + r) * 256 + kh + c] : 0.f;
+      gs[r][c] = (j0 + r < G) ? g[(size_t)(j0 + r) * 256 + kh + c] : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < 128; ++k) {
+      const float gv = gs[tx][k];
+      const float wa = ws[0][kh + k], wb = ws[1][kh + k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d = qs[ty * 4 + u][k] - gv;
+        const float s = d * d;
+        l0[u] = fmaf(wa, s, l0[u]);
+        l1[u] = fmaf(wb, s, l1[u]);
+      }
+    }
+  }
+  const float b0 = fold[Fold::CONSTS + 5], b1 = fold[Fold::CONSTS + 6];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + ty * 4 + u, j = j0 + tx;
+    if (i < Q && j < G) {
+      float2 o = make_float2(l0[u] + b0, l1[u] + b1);
+      *reinterpret_cast<float2*>(x5 + ((size_t)i * G + j) * 2) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- rank of a target item
+// CTA per query: margin of the target, then count items ranking before it.
+__global__ void __launch_bounds__(256) rank_of_target_kernel(const float* __restrict__ q, int Q,
+                                                             const float* __restrict__ g, int G,
+                                                             const int32_t* __restrict__ target,
+                                                             const float* __restrict__ fold,
+                                                             int32_t* __restrict__ out_rank,
+                                                             float* __restrict__ out_margin) {
+  __shared__ int cnt_s[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x;
+  const Slice w0 = load_slice(fold + Fold::LAST_W, lane);
+  const Slice w1 = load_slice(fold + Fold::LAST_W + 256, lane);
+  const float b0 = fold[Fold::CONSTS + 5], b1 = fold[Fold::CONSTS + 6];
+  const Slice qs = load_slice(q + (size_t)qi * 256, lane);
+  const int tj = target[qi];
+  float l0, l1;
+  pair_logits(qs, g + (size_t)tj * 256, w0, w1, b0, b1, lane, l0, l1);
+  const float dt = l1 - l0;
+  int cnt = 0;
+  for (int j = warp; j < G; j += 8) {
+    pair_logits(qs, g + (size_t)j * 256, w0, w1, b0, b1, lane, l0, l1);
+    if (wsort::ranks_before(l1 - l0, j, dt, tj)) ++cnt;
+  }
+  if (lane == 0) cnt_s[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += cnt_s[w];
+    out_rank[qi] = tot;
+    if (out_margin) out_margin[qi] = dt;
+  }
+}
+
+// ---------------------------------------------------------------- shard merge
+// warp per query; each input list is sorted best first with idx < 0 marking padding.
+__global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ scores,
+                                                         const float* __restrict__ margins,
+                                                         const int32_t* __restrict__ idx, int N, int Q, int k,
+                                                         float* __restrict__ out_score,
+                                                         float* __restrict__ out_margin,
+                                                         int32_t* __restrict__ out_idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= Q) return;
+  float d = -INFINITY, s = 0.f;
+  int id = INT_MAX;
+  for (int n = 0; n < N; ++n) {
+    const size_t base = ((size_t)n * Q + qi) * k;
+    if (n == 0) {
+      if (lane < k && idx[base + lane] >= 0) {
+        d = margins[base + lane];
+        s = scores[base + lane];
+        id = idx[base + lane];
+      }
+    } else {
+      const int e = 31 - lane;   // reversed: worst first
+      float od = -INFINITY, os = 0.f;
+      int oi = INT_MAX;
+      if (e < k && idx[base + e] >= 0) {
+        od = margins[base + e];
+        os = scores[base + e];
+        oi = idx[base + e];
+      }
+      if (wsort::ranks_before(od, oi, d, id)) {
+        d = od;
+        id = oi;
+        s = os;
+      }
+      wsort::merge32_rank(d, id, s, lane);
+    }
+  }
+  if (lane < k) {
+    const size_t o = (size_t)qi * k + lane;
+    const bool ok = id != INT_MAX;
+    out_score[o] = ok ? s : 0.f;
+    out_margin[o] = ok ? d : -INFINITY;
+    out_idx[o] = ok ? id : -1;
+  }
+}
+
+}  // namespace exact
+}  // namespace seam

@@ -1,0 +1,525 @@
+// C ABI of the B200-native SEAM Match-RCNN retrieval hot path (see include/seam_b200.h).
+// Host-side argument checking, workspace carving, tensor-map encoding and kernel launches.
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/seam_b200.h"
+#include "aggregate.cuh"
+#include "fold.cuh"
+#include "nlb_gemm.cuh"
+#include "score_exact.cuh"
+#include "score_tc.cuh"
+
+using namespace seam;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct seam_handle {
+  int device = 0;
+  int num_sms = 0;
+  float* fold = nullptr;            // folded weights (device)
+  bool have_scorer = false;
+  bool have_aggregator = false;
+  PFN_encodeTiled encode = nullptr;
+  uint64_t launches = 0;
+  char err[512] = {0};
+};
+
+static thread_local char g_create_err[256] = "";
+
+static int fail(seam_handle* h, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  if (h) vsnprintf(h->err, sizeof(h->err), fmt, ap);
+  else vsnprintf(g_create_err, sizeof(g_create_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define SEAM_CUDA(h, expr)                                                                             \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(h, SEAM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                                           \
+  } while (0)
+
+#define SEAM_LAUNCHED(h, name)                                                                      \
+  do {                                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                                           \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(h, SEAM_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));      \
+    ++(h)->launches;                                                                                \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" {
+
+int seam_abi_version(void) { return 1; }
+
+int seam_create(seam_handle** out, int device) {
+  if (!out) return fail(nullptr, SEAM_ERR_BAD_ARG, "seam_create: out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, SEAM_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev) return fail(nullptr, SEAM_ERR_BAD_ARG, "device %d out of range", device);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, SEAM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, SEAM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  seam_handle* h = new (std::nothrow) seam_handle();
+  if (!h) return fail(nullptr, SEAM_ERR_CUDA, "out of host memory");
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  DeviceGuard guard(device);
+  if ((e = cudaMalloc(&h->fold, sizeof(float) * Fold::TOTAL)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, SEAM_ERR_CUDA, "cudaMalloc(fold): %s", cudaGetErrorString(e));
+  }
+  cudaMemset(h->fold, 0, sizeof(float) * Fold::TOTAL);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    cudaFree(h->fold);
+    delete h;
+    return fail(nullptr, SEAM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  }
+  h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  // opt in to large dynamic shared memory once
+  cudaFuncSetAttribute(agg::aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(agg::Smem));
+  cudaFuncSetAttribute(score::score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)score::SMEM_BYTES);
+  cudaFuncSetAttribute(nlbgemm::nlb_full_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)((SEAM_MAX_T * 257 + 2 * SEAM_MAX_T) * sizeof(float)));
+  if ((e = cudaGetLastError()) != cudaSuccess) {
+    cudaFree(h->fold);
+    delete h;
+    return fail(nullptr, SEAM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return SEAM_OK;
+}
+
+void seam_destroy(seam_handle* h) {
+  if (!h) return;
+  {
+    DeviceGuard guard(h->device);
+    cudaFree(h->fold);
+  }
+  delete h;
+}
+
+const char* seam_last_error(const seam_handle* h) { return h ? h->err : g_create_err; }
+
+uint64_t seam_launch_count(const seam_handle* h) { return h ? h->launches : 0; }
+
+int seam_load_weights(seam_handle* h, const seam_weights* w, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!w) return fail(h, SEAM_ERR_BAD_ARG, "seam_load_weights: weights struct is null");
+  const float* const* ptrs = reinterpret_cast<const float* const*>(w);
+  for (int i = 0; i < 13; ++i)
+    if (!ptrs[i]) return fail(h, SEAM_ERR_BAD_ARG, "seam_load_weights: weight pointer %d is null", i);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  FoldIn in{w->theta_w, w->theta_b, w->phi_w, w->phi_b, w->g_w,    w->g_b,   w->W_w,
+            w->W_b,     w->concat_w, w->att_w, w->att_b, w->last_w, w->last_b};
+  fold_vectors_kernel<<<1, 256, 0, stream>>>(in, h->fold);
+  SEAM_LAUNCHED(h, "fold_vectors_kernel");
+  fold_matrix_kernel<<<256, 256, 0, stream>>>(w->W_w, w->g_w, h->fold);
+  SEAM_LAUNCHED(h, "fold_matrix_kernel");
+  h->have_scorer = h->have_aggregator = true;
+  return SEAM_OK;
+}
+
+int seam_load_scorer(seam_handle* h, const float* last_w, const float* last_b, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!last_w || !last_b) return fail(h, SEAM_ERR_BAD_ARG, "seam_load_scorer: null pointer");
+  DeviceGuard guard(h->device);
+  fold_scorer_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(last_w, last_b, h->fold);
+  SEAM_LAUNCHED(h, "fold_scorer_kernel");
+  h->have_scorer = true;
+  return SEAM_OK;
+}
+
+// ------------------------------------------------------------------------------ aggregation
+size_t seam_aggregate_workspace_bytes(int Q) {
+  if (Q <= 0) return 256;
+  return align_up((size_t)Q * 256 * 4, 256) + align_up((size_t)Q * 2 * 4, 256);
+}
+
+int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const int32_t* lens, int Tmax, int Q,
+                   int64_t frame_stride, int64_t track_stride, float* out, float* att, void* workspace,
+                   size_t workspace_bytes, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_aggregator) return fail(h, SEAM_ERR_STATE, "seam_aggregate: weights not loaded");
+  if (Q < 0 || Tmax < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: negative size");
+  if (Q == 0) return SEAM_OK;
+  if (!out) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: out is null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  if (Tmax == 0) {   // only the dummy row: every track is empty -> zero descriptors
+    SEAM_CUDA(h, cudaMemsetAsync(out, 0, (size_t)Q * 256 * 4, stream));
+    return SEAM_OK;
+  }
+  if (Tmax > SEAM_MAX_T) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: Tmax=%d exceeds %d", Tmax, SEAM_MAX_T);
+  if (!seq || !workspace) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: null pointer");
+  if (!aligned16(seq) || !aligned16(out) || (frame_stride & 3) || (track_stride & 3))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: seq/out must be 16-byte aligned, strides multiples of 4");
+  if (workspace_bytes < seam_aggregate_workspace_bytes(Q))
+    return fail(h, SEAM_ERR_STATE, "seam_aggregate: workspace too small (%zu < %zu)", workspace_bytes,
+                seam_aggregate_workspace_bytes(Q));
+  float* R = static_cast<float*>(workspace);
+  float* sv = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up((size_t)Q * 256 * 4, 256));
+
+  agg::Params p;
+  p.seq = seq;
+  p.mask = mask;
+  p.lens = lens;
+  p.Tmax = Tmax;
+  p.Q = Q;
+  p.NT = agg::ROWS_MAX / Tmax;
+  if (p.NT > agg::MAX_NT) p.NT = agg::MAX_NT;
+  if (p.NT < 1) p.NT = 1;
+  p.rows = p.NT * Tmax;
+  p.num_tiles = (Q + p.NT - 1) / p.NT;
+  p.frame_stride = frame_stride;
+  p.track_stride = track_stride;
+  p.fold = h->fold;
+  p.pooled = out;
+  p.R = R;
+  p.sv = sv;
+  p.att = att;
+  const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
+  agg::aggregate_kernel<<<grid, agg::THREADS, sizeof(agg::Smem), stream>>>(p);
+  SEAM_LAUNCHED(h, "aggregate_kernel");
+
+  nlbgemm::Params gp;
+  gp.pooled = out;
+  gp.R = R;
+  gp.sv = sv;
+  gp.fold = h->fold;
+  gp.out = out;
+  gp.rows = Q;
+  gp.T = 0;
+  dim3 ggrid((Q + nlbgemm::TM - 1) / nlbgemm::TM, 256 / nlbgemm::TN);
+  nlbgemm::nlb_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(gp);
+  SEAM_LAUNCHED(h, "nlb_gemm_simt_kernel");
+  return SEAM_OK;
+}
+
+size_t seam_nlb_workspace_bytes(int B, int T) {
+  if (B <= 0 || T <= 0) return 256;
+  const size_t rows = (size_t)B * T;
+  return 2 * align_up(rows * 256 * 4, 256) + align_up(rows * 2 * 4, 256);
+}
+
+int seam_nlb_forward(seam_handle* h, const float* x, int B, int T, float* z, void* workspace, size_t workspace_bytes,
+                     void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_aggregator) return fail(h, SEAM_ERR_STATE, "seam_nlb_forward: weights not loaded");
+  if (B < 0 || T < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_nlb_forward: negative size");
+  if (B == 0 || T == 0) return SEAM_OK;
+  if (T > SEAM_MAX_T) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_nlb_forward: T=%d exceeds %d", T, SEAM_MAX_T);
+  if (!x || !z || !workspace) return fail(h, SEAM_ERR_BAD_ARG, "seam_nlb_forward: null pointer");
+  if (workspace_bytes < seam_nlb_workspace_bytes(B, T))
+    return fail(h, SEAM_ERR_STATE, "seam_nlb_forward: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const size_t rows = (size_t)B * T;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* Xt = reinterpret_cast<float*>(ws);
+  float* R = reinterpret_cast<float*>(ws + align_up(rows * 256 * 4, 256));
+  float* sv = reinterpret_cast<float*>(ws + 2 * align_up(rows * 256 * 4, 256));
+  const size_t smem = (size_t)(T * 257 + 2 * T) * sizeof(float);
+  nlbgemm::nlb_full_front_kernel<<<B, 256, smem, stream>>>(x, T, h->fold, Xt, R, sv);
+  SEAM_LAUNCHED(h, "nlb_full_front_kernel");
+  nlbgemm::Params gp;
+  gp.pooled = Xt;
+  gp.R = R;
+  gp.sv = sv;
+  gp.fold = h->fold;
+  gp.out = z;
+  gp.rows = (int)rows;
+  gp.T = T;
+  dim3 ggrid((unsigned)((rows + nlbgemm::TM - 1) / nlbgemm::TM), 256 / nlbgemm::TN);
+  nlbgemm::nlb_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(gp);
+  SEAM_LAUNCHED(h, "nlb_gemm_simt_kernel");
+  return SEAM_OK;
+}
+
+// ------------------------------------------------------------------------------ scorer
+int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float* cg, float* gstat, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_prepare_gallery: scorer weights not loaded");
+  if (G < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_prepare_gallery: negative size");
+  if (!gstat) return fail(h, SEAM_ERR_BAD_ARG, "seam_prepare_gallery: gstat is null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  SEAM_CUDA(h, cudaMemsetAsync(gstat, 0, 16, stream));
+  if (G == 0) return SEAM_OK;
+  if (!g || !g16 || !cg) return fail(h, SEAM_ERR_BAD_ARG, "seam_prepare_gallery: null pointer");
+  if (!aligned16(g) || !aligned16(g16)) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_prepare_gallery: 16-byte alignment");
+  exact::prep_gallery_kernel<<<(G + 7) / 8, 256, 0, stream>>>(g, G, h->fold, static_cast<__half*>(g16), cg, gstat);
+  SEAM_LAUNCHED(h, "prep_gallery_kernel");
+  return SEAM_OK;
+}
+
+struct ScorePlan {
+  int num_mtiles, ntiles_n, P, tpp, num_items;
+  size_t off_a16, off_rq, off_anorm, off_thr, off_cv, off_ci, off_cnt, off_rows, total;
+};
+
+static ScorePlan plan_score(int num_sms, int Q, int G) {
+  ScorePlan s;
+  s.num_mtiles = (Q + score::BM - 1) / score::BM;
+  s.ntiles_n = (G + score::BN - 1) / score::BN;
+  if (s.num_mtiles < 1) s.num_mtiles = 1;
+  if (s.ntiles_n < 1) s.ntiles_n = 1;
+  // Split the gallery sweep of each 128-query tile into P parts so the (tile, part) items
+  // fill the SMs in whole waves; each part costs a fixed overhead (buffer warm-up + flush).
+  const double overhead_tiles = 3.0;
+  int bestP = 1;
+  double best = 1e300;
+  const int pmax = s.ntiles_n < 64 ? s.ntiles_n : 64;
+  for (int P = 1; P <= pmax; ++P) {
+    const int tpp = (s.ntiles_n + P - 1) / P;
+    if ((s.ntiles_n + tpp - 1) / tpp != P) continue;   // would leave empty parts
+    if (tpp > 256) continue;                           // 16-bit column index inside a part
+    const long items = (long)s.num_mtiles * P;
+    const long waves = (items + num_sms - 1) / num_sms;
+    const double cost = waves * (tpp + overhead_tiles);
+    if (cost < best) {
+      best = cost;
+      bestP = P;
+    }
+  }
+  s.P = bestP;
+  s.tpp = (s.ntiles_n + s.P - 1) / s.P;
+  if (s.tpp > 256) {   // enormous galleries: more parts than the search range
+    s.tpp = 256;
+    s.P = (s.ntiles_n + 255) / 256;
+  }
+  s.num_items = s.num_mtiles * s.P;
+  size_t o = 0;
+  s.off_a16 = o;   o += align_up((size_t)Q * 256 * 2, 256);
+  s.off_rq = o;    o += align_up((size_t)Q * 4, 256);
+  s.off_anorm = o; o += align_up((size_t)Q * 4, 256);
+  s.off_thr = o;   o += align_up((size_t)Q * 4, 256);
+  s.off_cv = o;    o += align_up((size_t)Q * s.P * score::KP * 4, 256);
+  s.off_ci = o;    o += align_up((size_t)Q * s.P * score::KP * 4, 256);
+  s.off_cnt = o;   o += 256;
+  s.off_rows = o;  o += align_up((size_t)Q * 4, 256);
+  s.total = o;
+  return s;
+}
+
+size_t seam_score_workspace_bytes(const seam_handle* h, int Q, int G, int k) {
+  (void)k;
+  if (!h || Q <= 0 || G <= 0) return 256;
+  return plan_score(h->num_sms, Q, G).total;
+}
+
+int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out) {
+  if (!h || !out || Q <= 0 || G <= 0) return SEAM_ERR_BAD_ARG;
+  const ScorePlan s = plan_score(h->num_sms, Q, G);
+  const int64_t v[14] = {s.num_mtiles, s.ntiles_n, s.P, s.tpp, s.num_items, (int64_t)s.off_a16, (int64_t)s.off_rq,
+                         (int64_t)s.off_anorm, (int64_t)s.off_thr, (int64_t)s.off_cv, (int64_t)s.off_ci,
+                         (int64_t)s.off_cnt, (int64_t)s.off_rows, (int64_t)s.total};
+  for (int i = 0; i < 14; ++i) out[i] = v[i];
+  return SEAM_OK;
+}
+
+__global__ void fill_empty_topk_kernel(float* s, float* d, int32_t* i, size_t n) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    s[t] = 0.f;
+    d[t] = -INFINITY;
+    i[t] = -1;
+  }
+}
+
+static int encode_map_fp16_rows(seam_handle* h, CUtensorMap* map, const void* base, int rows, int box_rows) {
+  const cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {256 * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)score::BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, SEAM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SEAM_OK;
+}
+
+int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const void* g16, const float* cg,
+                    const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin,
+                    int32_t* out_idx, int32_t* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_score_topk: scorer weights not loaded");
+  if (Q < 0 || G < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_topk: negative size");
+  if (k < 1 || k > SEAM_MAX_K) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_topk: k=%d outside [1,%d]", k, SEAM_MAX_K);
+  if (Q == 0) return SEAM_OK;
+  if (!out_score || !out_margin || !out_idx) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_topk: null output");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  if (stats) SEAM_CUDA(h, cudaMemsetAsync(stats, 0, 16, stream));
+  if (G == 0) {
+    const size_t n = (size_t)Q * k;
+    fill_empty_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out_score, out_margin, out_idx, n);
+    SEAM_LAUNCHED(h, "fill_empty_topk_kernel");
+    return SEAM_OK;
+  }
+  if (!q || !g || !g16 || !cg || !gstat || !workspace) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_topk: null pointer");
+  if (!aligned16(q) || !aligned16(g) || !aligned16(g16) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_topk: q/g/g16 need 16-byte, workspace 256-byte alignment");
+  const ScorePlan s = plan_score(h->num_sms, Q, G);
+  if (workspace_bytes < s.total)
+    return fail(h, SEAM_ERR_STATE, "seam_score_topk: workspace too small (%zu < %zu)", workspace_bytes, s.total);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  __half* a16 = reinterpret_cast<__half*>(ws + s.off_a16);
+  float* rq = reinterpret_cast<float*>(ws + s.off_rq);
+  float* anorm = reinterpret_cast<float*>(ws + s.off_anorm);
+  uint32_t* thr = reinterpret_cast<uint32_t*>(ws + s.off_thr);
+  float* cand_v = reinterpret_cast<float*>(ws + s.off_cv);
+  int32_t* cand_i = reinterpret_cast<int32_t*>(ws + s.off_ci);
+  int32_t* counters = reinterpret_cast<int32_t*>(ws + s.off_cnt);
+  int32_t* frows = reinterpret_cast<int32_t*>(ws + s.off_rows);
+
+  exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, counters);
+  SEAM_LAUNCHED(h, "prep_queries_kernel");
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = encode_map_fp16_rows(h, &tmA, a16, Q, score::BM)) != SEAM_OK) return rc;
+  if ((rc = encode_map_fp16_rows(h, &tmB, g16, G, score::BN)) != SEAM_OK) return rc;
+  score::Params sp;
+  sp.Q = Q;
+  sp.G = G;
+  sp.P = s.P;
+  sp.tiles_per_part = s.tpp;
+  sp.num_mtiles = s.num_mtiles;
+  sp.ntiles_n = s.ntiles_n;
+  sp.num_items = s.num_items;
+  sp.cg = cg;
+  sp.thr_global = thr;
+  sp.cand_v = cand_v;
+  sp.cand_i = cand_i;
+  const int grid = s.num_items < h->num_sms ? s.num_items : h->num_sms;
+  score::score_topk_kernel<<<grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+  SEAM_LAUNCHED(h, "score_topk_kernel");
+
+  exact::RescoreParams rp;
+  rp.q = q;
+  rp.g = g;
+  rp.fold = h->fold;
+  rp.cand_v = cand_v;
+  rp.cand_i = cand_i;
+  rp.rq = rq;
+  rp.anorm = anorm;
+  rp.gstat = gstat;
+  rp.Q = Q;
+  rp.G = G;
+  rp.P = s.P;
+  rp.k = k;
+  rp.index_offset = index_offset;
+  rp.out_score = out_score;
+  rp.out_margin = out_margin;
+  rp.out_idx = out_idx;
+  rp.counters = counters;
+  rp.fallback_rows = frows;
+  exact::rescore_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(rp);
+  SEAM_LAUNCHED(h, "rescore_kernel");
+
+  exact::ExactParams ep;
+  ep.q = q;
+  ep.g = g;
+  ep.fold = h->fold;
+  ep.Q = Q;
+  ep.G = G;
+  ep.k = k;
+  ep.index_offset = index_offset;
+  ep.count = counters;
+  ep.rows = frows;
+  ep.out_score = out_score;
+  ep.out_margin = out_margin;
+  ep.out_idx = out_idx;
+  exact::exact_topk_kernel<<<2 * h->num_sms, 256, 0, stream>>>(ep);
+  SEAM_LAUNCHED(h, "exact_topk_kernel");
+  if (stats) SEAM_CUDA(h, cudaMemcpyAsync(stats, counters, 4, cudaMemcpyDeviceToDevice, stream));
+  return SEAM_OK;
+}
+
+int seam_score_dense(seam_handle* h, const float* q, int Q, const float* g, int G, float* x5, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_score_dense: scorer weights not loaded");
+  if (Q < 0 || G < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_dense: negative size");
+  if (Q == 0 || G == 0) return SEAM_OK;
+  if (!q || !g || !x5) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_dense: null pointer");
+  if ((reinterpret_cast<uintptr_t>(x5) & 7u)) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_dense: x5 alignment");
+  DeviceGuard guard(h->device);
+  dim3 grid((G + 31) / 32, (Q + 31) / 32);
+  if (grid.y > 65535) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_dense: Q too large for the dense path");
+  exact::dense_logits_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(q, Q, g, G, h->fold, x5);
+  SEAM_LAUNCHED(h, "dense_logits_kernel");
+  return SEAM_OK;
+}
+
+int seam_rank_of_target(seam_handle* h, const float* q, int Q, const float* g, int G, const int32_t* target,
+                        int32_t* out_rank, float* out_margin, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_rank_of_target: scorer weights not loaded");
+  if (Q < 0 || G <= 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_of_target: bad size");
+  if (Q == 0) return SEAM_OK;
+  if (!q || !g || !target || !out_rank) return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_of_target: null pointer");
+  if (!aligned16(q) || !aligned16(g)) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_of_target: 16-byte alignment");
+  DeviceGuard guard(h->device);
+  exact::rank_of_target_kernel<<<Q, 256, 0, static_cast<cudaStream_t>(stream_)>>>(q, Q, g, G, target, h->fold,
+                                                                                   out_rank, out_margin);
+  SEAM_LAUNCHED(h, "rank_of_target_kernel");
+  return SEAM_OK;
+}
+
+int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, const int32_t* idx, int N, int Q,
+                    int k, float* out_score, float* out_margin, int32_t* out_idx, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (N < 1 || Q < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_merge_topk: bad size");
+  if (k < 1 || k > SEAM_MAX_K) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_merge_topk: k=%d outside [1,%d]", k, SEAM_MAX_K);
+  if (Q == 0) return SEAM_OK;
+  if (!scores || !margins || !idx || !out_score || !out_margin || !out_idx)
+    return fail(h, SEAM_ERR_BAD_ARG, "seam_merge_topk: null pointer");
+  DeviceGuard guard(h->device);
+  exact::merge_topk_kernel<<<(Q + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      scores, margins, idx, N, Q, k, out_score, out_margin, out_idx);
+  SEAM_LAUNCHED(h, "merge_topk_kernel");
+  return SEAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+"""Thin torch-facing wrapper over the C ABI: one ``SeamEngine`` per CUDA device.
+
+PyTorch is used for device memory, streams and tensor plumbing only; all arithmetic of
+the hot path runs in the hand-written kernels behind ``libseam_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Mapping, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SeamError, SeamWeights, WEIGHT_KEYS
+
+D_MODEL = 256
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class PreparedGallery:
+    """A gallery shard resident on the device with its tensor-core operands.
+
+    g    (G,256) fp32   the shop descriptors (x3_2 of models/match_head.py:131/156)
+    g16  (G,256) fp16   operand of the tcgen05 pass
+    cg   (G)     fp32   dw . g_j^2
+    gstat (4)    fp32   [max_j ||g_j||, fp16-overflow flag, -, -]
+    """
+    g: torch.Tensor
+    g16: torch.Tensor
+    cg: torch.Tensor
+    gstat: torch.Tensor
+    index_offset: int = 0
+
+    @property
+    def G(self) -> int:
+        return self.g.shape[0]
+
+
+class SeamEngine:
+    """Owns a ``seam_handle`` (folded weights) for one device."""
+
+    def __init__(self, device="cuda:0"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise SeamError(2, f"SeamEngine needs a CUDA device, got {device}; there is no CPU path")
+        if not torch.cuda.is_available():
+            raise SeamError(3, "no CUDA device is visible; the SEAM hot path has no CPU fallback")
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.seam_create(C.byref(h), self.device.index)
+        if rc != 0:
+            raise SeamError(rc, self._lib.seam_last_error(None).decode())
+        self._h = h
+        self._ws: Dict[str, torch.Tensor] = {}
+        self._weights_key = None
+        self._weight_refs = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.seam_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise SeamError(rc, self._lib.seam_last_error(self._h).decode())
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _workspace(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            self._ws[name] = t
+        return t
+
+    def _f32(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        return t
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.seam_launch_count(self._h))
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, state: Mapping[str, torch.Tensor], prefix: str = "") -> None:
+        """Upload + fold the hot-path weights from a (possibly prefixed) state_dict.
+
+        Accepts ``TemporalAggregationNLB().state_dict()`` keys, optionally prefixed with
+        ``roi_heads.temporal_aggregator.`` as in a full checkpoint
+        (models/video_matchrcnn.py:37, evaluate_movingfashion.py:502-503).
+        """
+        tensors = {}
+        for field, key in WEIGHT_KEYS.items():
+            k = prefix + key
+            if k not in state:
+                raise KeyError(f"state_dict is missing '{k}'")
+            tensors[field] = self._f32(state[k].detach(), k)
+        w = SeamWeights(**{f: tensors[f].data_ptr() for f in SeamWeights.FIELDS})
+        self._check(self._lib.seam_load_weights(self._h, C.byref(w), self._stream()))
+        self._weight_refs = tensors   # keep alive until the fold kernels have run
+
+    def load_scorer(self, last_w: torch.Tensor, last_b: torch.Tensor) -> None:
+        """Only ``last`` (e.g. ``match_predictor.last`` for the per-frame scorers)."""
+        lw, lb = self._f32(last_w.detach(), "last_w"), self._f32(last_b.detach(), "last_b")
+        if lw.shape != (2, D_MODEL) or lb.shape != (2,):
+            raise ValueError("last.weight must be (2,256) and last.bias (2,)")
+        self._check(self._lib.seam_load_scorer(self._h, lw.data_ptr(), lb.data_ptr(), self._stream()))
+        self._weight_refs = (lw, lb)
+
+    # ------------------------------------------------------------------ (a) aggregation
+    def aggregate(self, seq: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                  lens: Optional[torch.Tensor] = None, getatt: bool = False):
+        """x3_1b (and attention weights) from the padded time-major track tensor.
+
+        seq (1+Tmax, Q, 256) fp32 with dummy row 0, mask (Q, 1+Tmax) bool (True = padding):
+        the arguments ``x3_1_seq`` / ``x3_1_mask`` of models/match_head.py:90, :133-154.
+        """
+        if seq.dim() != 3 or seq.shape[2] != D_MODEL:
+            raise ValueError(f"x3_1_seq must be (1+Tmax, Q, 256), got {tuple(seq.shape)}")
+        if seq.device != self.device or seq.dtype != torch.float32:
+            seq = seq.to(device=self.device, dtype=torch.float32)
+        if seq.stride(2) != 1 or seq.stride(0) % 4 or seq.stride(1) % 4:
+            seq = seq.contiguous()
+        Tmax, Q = seq.shape[0] - 1, seq.shape[1]
+        if Tmax > _lib.SEAM_MAX_T:
+            raise SeamError(2, f"Tmax={Tmax} exceeds the supported {_lib.SEAM_MAX_T} frames per track")
+        m8 = None
+        if mask is not None:
+            if tuple(mask.shape) != (Q, 1 + Tmax):
+                raise ValueError(f"x3_1_mask must be (Q, 1+Tmax)={Q, 1 + Tmax}, got {tuple(mask.shape)}")
+            m8 = mask.to(device=self.device, dtype=torch.bool).contiguous().view(torch.uint8)
+        l32 = None
+        if lens is not None:
+            l32 = lens.to(device=self.device, dtype=torch.int32).contiguous()
+        out = torch.empty((Q, D_MODEL), dtype=torch.float32, device=self.device)
+        att = torch.empty((Q, Tmax), dtype=torch.float32, device=self.device) if getatt else None
+        nbytes = int(self._lib.seam_aggregate_workspace_bytes(Q))
+        ws = self._workspace("agg", nbytes)
+        self._check(self._lib.seam_aggregate(self._h, seq.data_ptr(), _ptr(m8), _ptr(l32), Tmax, Q,
+                                             seq.stride(0), seq.stride(1), out.data_ptr(), _ptr(att),
+                                             ws.data_ptr(), ws.numel(), self._stream()))
+        return (out, att) if getatt else out
+
+    def nlb_forward(self, x: torch.Tensor) -> torch.Tensor:
+        """NONLocalBlock1D.forward (models/nlb.py:66-101): (B,256,T) -> (B,256,T)."""
+        if x.dim() != 3 or x.shape[1] != D_MODEL:
+            raise ValueError(f"x must be (B,256,T), got {tuple(x.shape)}")
+        x = self._f32(x, "x")
+        B, _, T = x.shape
+        if T > _lib.SEAM_MAX_T:
+            raise SeamError(2, f"T={T} exceeds the supported {_lib.SEAM_MAX_T}")
+        z = torch.empty_like(x)
+        nbytes = int(self._lib.seam_nlb_workspace_bytes(B, T))
+        ws = self._workspace("nlb", nbytes)
+        self._check(self._lib.seam_nlb_forward(self._h, x.data_ptr(), B, T, z.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), self._stream()))
+        return z
+
+    # ------------------------------------------------------------------ (b)+(c) scorer
+    def prepare_gallery(self, g: torch.Tensor, index_offset: int = 0) -> PreparedGallery:
+        if g.dim() != 2 or g.shape[1] != D_MODEL:
+            raise ValueError(f"gallery must be (G,256), got {tuple(g.shape)}")
+        g = self._f32(g, "gallery")
+        G = g.shape[0]
+        g16 = torch.empty((G, D_MODEL), dtype=torch.float16, device=self.device)
+        cg = torch.empty((max(G, 1),), dtype=torch.float32, device=self.device)
+        gstat = torch.empty((4,), dtype=torch.float32, device=self.device)
+        self._check(self._lib.seam_prepare_gallery(self._h, g.data_ptr(), G, g16.data_ptr(), cg.data_ptr(),
+                                                   gstat.data_ptr(), self._stream()))
+        return PreparedGallery(g=g, g16=g16, cg=cg, gstat=gstat, index_offset=index_offset)
+
+    def score_topk(self, q: torch.Tensor, gallery: PreparedGallery, k: int,
+                   return_stats: bool = False):
+        """Best k gallery items per query: (scores (Q,k), margins (Q,k), idx (Q,k) int32)."""
+        if q.dim() != 2 or q.shape[1] != D_MODEL:
+            raise ValueError(f"queries must be (Q,256), got {tuple(q.shape)}")
+        q = self._f32(q, "queries")
+        Q, G = q.shape[0], gallery.G
+        k = int(k)
+        sc = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        mg = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        ix = torch.empty((Q, k), dtype=torch.int32, device=self.device)
+        stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        nbytes = int(self._lib.seam_score_workspace_bytes(self._h, Q, G, k))
+        ws = self._workspace("score", nbytes)
+        self._check(self._lib.seam_score_topk(self._h, q.data_ptr(), Q, gallery.g.data_ptr(),
+                                              gallery.g16.data_ptr(), gallery.cg.data_ptr(),
+                                              gallery.gstat.data_ptr(), G, int(gallery.index_offset), k,
+                                              sc.data_ptr(), mg.data_ptr(), ix.data_ptr(), stats.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), self._stream()))
+        if return_stats:
+            return sc, mg, ix, stats
+        return sc, mg, ix
+
+    def score_plan(self, Q: int, G: int) -> Dict[str, int]:
+        """Work decomposition + workspace layout seam_score_topk will use for (Q,G)."""
+        out = (C.c_int64 * 14)()
+        self._check(self._lib.seam_score_plan(self._h, int(Q), int(G), out))
+        names = ("query_tiles", "gallery_tiles", "parts", "tiles_per_part", "items", "off_a16", "off_rq",
+                 "off_anorm", "off_thr", "off_cand_v", "off_cand_i", "off_counters", "off_rows", "bytes")
+        return dict(zip(names, [int(v) for v in out]))
+
+    def score_dense(self, q: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+        """x5 (Q,G,2) = last((q-g)^2): models/match_head.py:160-162."""
+        q, g = self._f32(q, "queries"), self._f32(g, "gallery")
+        x5 = torch.empty((q.shape[0], g.shape[0], 2), dtype=torch.float32, device=self.device)
+        self._check(self._lib.seam_score_dense(self._h, q.data_ptr(), q.shape[0], g.data_ptr(), g.shape[0],
+                                               x5.data_ptr(), self._stream()))
+        return x5
+
+    def rank_of_target(self, q: torch.Tensor, g: torch.Tensor, target: torch.Tensor
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Rank (0 = best) of gallery row target[i] for query i: evaluate_movingfashion.py:268-269."""
+        q, g = self._f32(q, "queries"), self._f32(g, "gallery")
+        t32 = target.to(device=self.device, dtype=torch.int32).contiguous()
+        Q = q.shape[0]
+        if t32.shape != (Q,):
+            raise ValueError("target must have one gallery row per query")
+        if Q and (int(t32.min()) < 0 or int(t32.max()) >= g.shape[0]):
+            raise ValueError("target index out of range")
+        rank = torch.empty((Q,), dtype=torch.int32, device=self.device)
+        margin = torch.empty((Q,), dtype=torch.float32, device=self.device)
+        self._check(self._lib.seam_rank_of_target(self._h, q.data_ptr(), Q, g.data_ptr(), g.shape[0],
+                                                  t32.data_ptr(), rank.data_ptr(), margin.data_ptr(),
+                                                  self._stream()))
+        return rank, margin
+
+    def merge_topk(self, scores: torch.Tensor, margins: torch.Tensor, idx: torch.Tensor):
+        """Merge (N,Q,k) per-shard lists into (Q,k)."""
+        N, Q, k = scores.shape
+        scores, margins = self._f32(scores, "scores"), self._f32(margins, "margins")
+        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        sc = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        mg = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        ix = torch.empty((Q, k), dtype=torch.int32, device=self.device)
+        self._check(self._lib.seam_merge_topk(self._h, scores.data_ptr(), margins.data_ptr(), idx.data_ptr(),
+                                              N, Q, k, sc.data_ptr(), mg.data_ptr(), ix.data_ptr(),
+                                              self._stream()))
+        return sc, mg, ix
+
+
+_engines: Dict[int, SeamEngine] = {}
+
+
+def get_engine(device="cuda") -> SeamEngine:
+    """Process-wide engine for a device (created on first use)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise SeamError(2, f"the SEAM hot path runs on CUDA only (got {device}); there is no CPU fallback")
+    if not torch.cuda.is_available():
+        raise SeamError(3, "no CUDA device is visible; the SEAM hot path has no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = SeamEngine(torch.device("cuda", idx))
+    return _engines[idx]
