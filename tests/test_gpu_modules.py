@@ -1,0 +1,143 @@
+"""The drop-in modules on the GPU: same signatures, state_dict keys and return tuples as the
+reference's (models/match_head.py:47-169, models/nlb.py:104-109), results against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import seam_match_rcnn_b200 as pkg
+from oracle import seam_oracle as so
+from util import GOLDEN_CASES, TOL_ATT, TOL_EMB, TOL_LOGIT, case_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def model(weights):
+    m = pkg.TemporalAggregationNLB().to(DEV).eval()
+    missing, unexpected = m.load_state_dict(weights, strict=False)
+    assert not unexpected
+    return m
+
+
+@pytest.mark.parametrize("name", ["cfg1", "ragged", "t1"])
+def test_seq_branch_tuple(name, model, weights, golden):
+    case = GOLDEN_CASES[name]
+    seq, mask, _, gal = case_inputs(case, weights)
+    out = model(None, None, None, x3_1_seq=seq.to(DEV), x3_1_mask=mask.to(DEV), x3_2=gal.to(DEV), getatt=True)
+    assert len(out) == 7
+    x3_1b, x3_2, x5, s_out, m_out, ids, att = out
+    assert ids.shape == (1, 2) and x5.shape == (case["Q"], case["G"], 2)
+    assert (x3_1b.cpu() - torch.from_numpy(golden[f"{name}.x3_1b"])).abs().max() <= TOL_EMB
+    assert (x5[:4].cpu() - torch.from_numpy(golden[f"{name}.x5_head"])).abs().max() <= TOL_LOGIT
+    assert len(att) == case["Q"]
+    for i, p in enumerate(att):
+        n = int(golden[f"{name}.lens"][i])
+        assert p.shape == (n, 1)
+        assert (p[:, 0].cpu() - torch.from_numpy(golden[f"{name}.att"][i, :n])).abs().max() <= TOL_ATT
+    assert len(model(None, None, None, x3_1_seq=seq.to(DEV), x3_1_mask=mask.to(DEV), x3_2=gal.to(DEV))) == 6
+
+
+def test_eval_script_call_shape(model, weights):
+    """The exact call of evaluate_movingfashion.py:253-262: one track, 1-D x3_2, [0][0]."""
+    seq, mask, _ = so.synth_tracks(1, 10, seed=9)
+    shop = torch.randn(256)
+    r = model(None, None, None, x3_1_seq=seq.to(DEV), x3_1_mask=mask.to(DEV), x3_2=shop.to(DEV))
+    ref = so.forward_seq_branch(seq, mask, shop, weights)
+    assert (r[0][0].cpu() - ref[0][0]).abs().max() <= TOL_EMB
+    assert r[2].shape == ref[2].shape == (1, 1, 2)
+    assert (r[2].cpu() - ref[2]).abs().max() <= TOL_LOGIT
+
+
+def test_score_topk_entry(model, weights, golden):
+    case = GOLDEN_CASES["cfg1"]
+    seq, mask, _, gal = case_inputs(case, weights)
+    scores, idx = model.score_topk(seq.to(DEV), mask.to(DEV), gal.to(DEV), k=20)
+    assert idx.dtype == torch.int64
+    assert torch.equal(idx.cpu(), torch.from_numpy(golden["cfg1.topk_idx"]).long())
+    assert (scores.cpu() - torch.from_numpy(golden["cfg1.topk_score"])).abs().max() <= 1e-5
+    with pytest.raises(pkg.SeamError):          # the dense tuple is refused beyond the size limit
+        model(None, None, None, x3_1_seq=torch.zeros(2, 9000, 256, device=DEV),
+              x3_1_mask=torch.zeros(9000, 2, dtype=torch.bool, device=DEV), x3_2=torch.zeros(9000, 256, device=DEV))
+
+
+def test_x_branch_groups_tracks_like_the_reference(model, weights):
+    """x-branch (models/match_head.py:92-131): ROI features -> tower -> group street rows by id."""
+    torch.manual_seed(0)
+    x = torch.randn(9, 256, 14, 14, device=DEV)
+    types = torch.tensor([1, 0, 0, 0, 1, 0, 0, 0, 0])
+    ids = torch.tensor([0, 5, 2, 5, 0, 2, 5, 9, 2])
+    x3_1b, x3_2, x5, seq, mask, out_ids = model(x, types, ids)
+    x3 = model.embed(x)
+    st_ids = ids[types == 0]
+    uniq = st_ids.unique()
+    assert seq.shape == (1 + 3, 3, 256) and mask.shape == (3, 4)
+    for i, idd in enumerate(uniq):
+        rows = x3[types.to(DEV) == 0][st_ids.to(DEV) == idd]
+        n = rows.shape[0]
+        assert torch.equal(seq[1:1 + n, i], rows) and not mask[i, :n + 1].any() and mask[i, n + 1:].all()
+    ref, _ = so.aggregate_tracks(seq.cpu(), mask.cpu(), weights)
+    assert (x3_1b.cpu() - ref).abs().max() <= TOL_EMB
+    assert x5.shape == (3, 2, 2) and torch.equal(x3_2, x3[types.to(DEV) == 1])
+    assert torch.equal(out_ids.cpu(), st_ids)
+    # no street items at all -> None outputs (match_head.py:126-128, 163-164)
+    r = model(x[:2], torch.tensor([1, 1]), torch.tensor([0, 1]))
+    assert r[0] is None and r[2] is None
+
+
+def test_match_predictor_forward(weights):
+    m = pkg.MatchPredictor().to(DEV).eval()
+    m.last.load_state_dict({"weight": weights["last.weight"], "bias": weights["last.bias"]})
+    torch.manual_seed(1)
+    x = torch.randn(7, 256, 14, 14, device=DEV)
+    types = torch.tensor([0, 0, 1, 1, 1, 0, 1])
+    x3, x5 = m(x, types)
+    assert x3.shape == (7, 256) and x5.shape == (3, 4, 2)
+    ref = so.pair_logits(x3[types.to(DEV) == 0].cpu(), x3[types.to(DEV) == 1].cpu(), weights)
+    assert (x5.cpu() - ref).abs().max() <= TOL_LOGIT
+
+
+def test_nonlocal_block_module(weights, golden):
+    nlb = pkg.NONLocalBlock1D(in_channels=256, sub_sample=False, bn_layer=False).to(DEV).eval()
+    x = torch.from_numpy(golden["nlb.t7.x"]).to(DEV)
+    assert torch.equal(nlb(x), x)               # zero-initialised W: identity (models/nlb.py:48-49)
+    nlb.load_state_dict({k[len("newnlb."):]: v for k, v in weights.items() if k.startswith("newnlb.")})
+    assert (nlb(x).cpu() - torch.from_numpy(golden["nlb.t7.z"])).abs().max() <= TOL_EMB
+    with pytest.raises(NotImplementedError):
+        pkg.NONLocalBlock1D(in_channels=64)
+
+
+def test_weight_updates_are_picked_up(model, weights):
+    seq, mask, _ = so.synth_tracks(4, 5, seed=1)
+    a = model.aggregate(seq.to(DEV), mask.to(DEV)).clone()
+    saved = model.newnlb.W.weight.detach().clone()
+    with torch.no_grad():
+        model.newnlb.W.weight.mul_(0.5)
+    b = model.aggregate(seq.to(DEV), mask.to(DEV))
+    assert not torch.equal(a, b)
+    w2 = dict(weights)
+    w2["newnlb.W.weight"] = weights["newnlb.W.weight"] * 0.5
+    ref, _ = so.aggregate_tracks(seq, mask, w2)
+    assert (b.cpu() - ref).abs().max() <= TOL_EMB
+    with torch.no_grad():
+        model.newnlb.W.weight.copy_(saved)
+    model.nlb = False                            # reference flag: skip the block (match_head.py:113)
+    c = model.aggregate(seq.to(DEV), mask.to(DEV))
+    ref0, _ = so.aggregate_tracks(seq, mask, weights, use_nlb=False)
+    assert (c.cpu() - ref0).abs().max() <= TOL_EMB
+    model.nlb = True
+
+
+def test_evaluate_aggregated_report(model, weights):
+    """evaluate_movingfashion.py:252-277 for all products at once."""
+    Q, T, G = 40, 6, 120
+    seq, mask, _ = so.synth_tracks(Q, T, seed=2, ragged=(1, 6))
+    qref, _ = so.aggregate_tracks(seq, mask, weights)
+    gal = so.synth_gallery(G, 2, None)
+    target = torch.arange(Q) * 2
+    eng = model._engine_for(torch.device(DEV))
+    rep = pkg.evaluate_aggregated(eng, seq.to(DEV), mask.to(DEV), gal.to(DEV), target)
+    x5 = so.pair_logits(qref, gal, weights)
+    ranks = so.rank_of_target(x5, target)
+    assert torch.equal(rep.ranks.cpu().long(), ranks)
+    assert rep.hits == [int((ranks < k).sum()) for k in (1, 5, 10, 20)]
