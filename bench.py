@@ -1,0 +1,347 @@
+"""Benchmark of the SEAM retrieval hot path (aggregation -> pair scorer -> top-k) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+Prints ONE JSON line (rank 0).  A "step" is one pass of the hot path over one batch of synthetic
+tracks: BASELINE.json configs[1] (15,000 tracks x 10 frames vs 15,000 shop items, k=20) at N=1.
+For N>1 the gallery is sharded (15,000 rows PER GPU, weak scaling), aggregation is split by
+query and the per-shard top-k lists are all-gathered over NCCL and merged.
+
+metric        pair scores/sec = Q*G / (device time of aggregation + scorer + top-k [+ collectives])
+value         inputs already resident in HBM, CUDA-event timed, max over ranks
+e2e           same metric through the public Python API from pinned HOST buffers: H2D of the
+              tracks, mask and gallery shard, gallery preparation, the hot path, D2H of the results
+roofline      dominant kernel (score_topk_kernel, tensor-bound): 512 FLOP per pair
+cpu_baseline  the oracle (CPU port of the reference's torch fp32 module path) on the host cores
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+Q_TRACKS, T_FRAMES, G_PER_GPU, TOPK = 15000, 10, 15000, 20
+FLOP_PER_PAIR = 512               # 2 * 256: single-channel dw GEMM
+METRIC, UNIT = "pair_scores_per_sec", "pairs/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops"], "tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path (torch fp32 module path + softmax +
+    ranking), restated in oracle/seam_oracle.py and checked against the reference's outputs
+    (tests/golden).  The reference is Python and does not travel to the GPU box, hence the port.
+    Each step: a bounded sample of the workload -- SAMPLE_Q tracks against the full gallery."""
+    from oracle import seam_oracle as so
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = so.random_weights(0)
+    G = G_PER_GPU * args.gpus
+    sample_q = 64
+    seq, mask, _ = so.synth_tracks(sample_q, T_FRAMES, seed=1)
+    gal = so.synth_gallery(G, 1, None)
+
+    def step():
+        q, _ = so.aggregate_tracks(seq, mask, w)
+        x5 = so.pair_logits(q, gal, w)
+        return so.rank_topk(x5, TOPK)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
+    value = sample_q * G / dt
+    sample = f"{sample_q} tracks x {T_FRAMES} frames vs {G} shop items per step (of {Q_TRACKS} tracks)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MovingFashion-scale eval: {Q_TRACKS} tracks x {T_FRAMES} frames vs {G} shop items, k={TOPK}",
+                   "sample": sample, "threads": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "queries_per_sec": sample_q / dt,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(budget_s=12.0):
+    """Oracle timed on the host cores on a bounded sample of the N=1 workload."""
+    from oracle import seam_oracle as so
+    cores = os.cpu_count() or 1
+    prev = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    w = so.random_weights(0)
+    chunk = 64
+    seq, mask, _ = so.synth_tracks(chunk, T_FRAMES, seed=1)
+    gal = so.synth_gallery(G_PER_GPU, 1, None)
+    with torch.no_grad():
+        def step():
+            q, _ = so.aggregate_tracks(seq, mask, w)
+            return so.rank_topk(so.pair_logits(q, gal, w), TOPK)
+        step()
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            step()
+            n += 1
+            if time.perf_counter() - t0 > budget_s or n >= 64:
+                break
+        dt = time.perf_counter() - t0
+    torch.set_num_threads(prev)
+    return {"value": n * chunk * G_PER_GPU / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} x ({chunk} tracks x {T_FRAMES} frames vs {G_PER_GPU} shop items), {dt:.1f} s",
+            "queries_per_sec": n * chunk / dt}
+
+
+def random_init_weights(dev):
+    """Random-init aggregator weights of the reference's architecture (default torch init
+    U(+-1/sqrt(fan_in)); newnlb.W re-drawn because the reference zero-initialises it, which
+    would make the block a no-op -- SURVEY.md section 0 item 2)."""
+    g = torch.Generator().manual_seed(0)
+
+    def u(shape, fan_in):
+        return ((torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5).to(dev)
+
+    w = {}
+    for n in ("g", "theta", "phi"):
+        w[f"newnlb.{n}.weight"], w[f"newnlb.{n}.bias"] = u((128, 256, 1), 256), u((128,), 256)
+    w["newnlb.W.weight"], w["newnlb.W.bias"] = u((256, 128, 1), 128), u((256,), 128)
+    w["newnlb.concat_project.0.weight"] = u((1, 256, 1, 1), 256)
+    w["attention_scorer.weight"], w["attention_scorer.bias"] = u((1, 256), 256), u((1,), 256)
+    w["last.weight"], w["last.bias"] = u((2, 256), 256), u((2,), 256)
+    return w
+
+
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import seam_match_rcnn_b200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = pkg.SeamEngine(dev)
+    eng.load_weights(random_init_weights(dev))
+    Q, T, Gs, k = Q_TRACKS, T_FRAMES, G_PER_GPU, TOPK
+    G = Gs * world
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    # host (pinned) inputs: this rank's slice of the tracks and its gallery shard
+    qlo, qhi = pkg.shard_bounds(Q, world, rank)
+    seq_h = torch.zeros(1 + T, qhi - qlo, 256).pin_memory()
+    seq_h[1:] = torch.randn(T, qhi - qlo, 256, generator=gen)
+    mask_h = torch.zeros(qhi - qlo, 1 + T, dtype=torch.bool).pin_memory()
+    gen_g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    gal_h = torch.randn(Gs, 256, generator=gen_g).pin_memory()
+    out_h = [torch.empty(Q, k).pin_memory(), torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int32).pin_memory()]
+    h2d = seq_h.numel() * 4 + mask_h.numel() + gal_h.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in out_h)
+
+    seq_d, mask_d, gal_d = seq_h.to(dev), mask_h.to(dev), gal_h.to(dev)
+    gallery = eng.prepare_gallery(gal_d, index_offset=rank * Gs)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def hot_path(seq, mask, gal):
+        q = eng.aggregate(seq, mask)
+        if world > 1:
+            q = pkg.all_gather_rows(q)
+        sc, mg, ix = eng.score_topk(q, gal, k)
+        if world > 1:
+            packs = []
+            for t in (sc, mg, ix):
+                outs = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(outs, t)
+                packs.append(torch.stack(outs, 0))
+            sc, mg, ix = eng.merge_topk(*packs)
+        return sc, mg, ix
+
+    def device_step():
+        return hot_path(seq_d, mask_d, gallery)
+
+    def e2e_step():
+        s = seq_h.to(dev, non_blocking=True)
+        m = mask_h.to(dev, non_blocking=True)
+        g = eng.prepare_gallery(gal_h.to(dev, non_blocking=True), index_offset=rank * Gs)
+        res = hot_path(s, m, g)
+        for dst, src in zip(out_h, res):
+            dst.copy_(src, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        total = 0.0
+        lc0 = eng.launch_count
+        for _ in range(steps):
+            flush.fill_(1)                   # evict L2 between timed iterations (not timed)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            barrier()
+            total += a.elapsed_time(b)
+        t = torch.tensor([total / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), eng.launch_count - lc0      # ms per step (max over ranks), kernels launched
+
+    warmup = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(device_step, args.steps, warmup)
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(e2e_step, args.steps, warmup)
+
+    # per-kernel durations (CUDA events inside the library, on the launching stream)
+    eng.profile(True)
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        device_step()
+    barrier()
+    prof = eng.profile_read()
+    eng.profile(False)
+    kern = {n: (tot / cnt if cnt else None) for n, (tot, cnt) in prof.items()}
+    peaks = measured_peaks()
+    pairs_per_gpu = Q * Gs
+    t_score = kern["score"]
+    t_agg = kern["aggregate"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("score_topk_kernel_dram_bytes_per_launch")
+    roofline = {
+        "kernel": "score_topk_kernel", "bound": "tensor",
+        "achieved": pairs_per_gpu * FLOP_PER_PAIR / (t_score * 1e-3) / 1e12, "peak": peaks["tflops"],
+        "unit": "TFLOP/s", "traffic": traffic, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
+        "avg_launch_ms": t_score,
+    }
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    agg_bytes = (qhi - qlo) * 1024 * (T + 1)
+    roofline_agg = {
+        "kernel": "aggregate_kernel", "bound": "hbm", "achieved": agg_bytes / (t_agg * 1e-3) / 1e9,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None, "peak_source": peaks["source"] + " copy",
+        "avg_launch_ms": t_agg,
+    }
+    roofline_agg["frac"] = roofline_agg["achieved"] / roofline_agg["peak"]
+
+    if rank == 0:
+        cpu = cpu_baseline() if world == 1 else None
+        line = {
+            "metric": METRIC, "value": Q * G / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 results (fp16 tcgen05 candidate pass, fp32 re-score)", "data": "synthetic",
+            "config": {"workload": f"MovingFashion-scale eval: {Q} tracks x {T} frames vs {G} shop items "
+                                   f"({Gs}/GPU), k={k}; aggregation + scoring + top-k",
+                       "l2": "256 MiB buffer written between timed iterations",
+                       "parallelism": f"gallery sharded x{world}, queries replicated" if world > 1 else "single GPU"},
+            "queries_per_sec": Q / (ms * 1e-3),
+            "e2e": {"value": Q * G / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "queries_per_sec": Q / (ms_e2e * 1e-3)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_aggregate": roofline_agg,
+            "kernel_ms": kern,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

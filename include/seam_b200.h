@@ -48,6 +48,22 @@ const char* seam_last_error(const seam_handle* h);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 uint64_t seam_launch_count(const seam_handle* h);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled, the library brackets each
+ * of its named kernels with CUDA events on the launching stream.  seam_profile_read waits
+ * for the recorded events of one kernel, returns their summed duration and count, and
+ * forgets them. */
+enum seam_kernel {
+  SEAM_KERNEL_AGGREGATE = 0,    /* K1a aggregate_kernel */
+  SEAM_KERNEL_NLB_GEMM = 1,     /* K1b */
+  SEAM_KERNEL_PREP_QUERIES = 2,
+  SEAM_KERNEL_SCORE = 3,        /* K2 score_topk_kernel (tcgen05) */
+  SEAM_KERNEL_RESCORE = 4,      /* K3b */
+  SEAM_KERNEL_EXACT = 5,        /* K3c exhaustive path */
+  SEAM_KERNEL_PREP_GALLERY = 6,
+};
+int seam_profile_enable(seam_handle* h, int enable);
+int seam_profile_read(seam_handle* h, int kernel, double* total_ms, int* launches);
+
 /* Hot-path weights, fp32, device pointers, in the reference's state_dict layout
  * (TemporalAggregationNLB().state_dict()):
  *   newnlb.{theta,phi,g}.weight (128,256,1) / .bias (128)      models/nlb.py:34,51,54

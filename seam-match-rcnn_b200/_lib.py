@@ -16,6 +16,8 @@ _HEADER = os.path.join(os.path.dirname(_build.HERE), "include", "seam_b200.h")
 
 SEAM_OK = 0
 STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "STATE"}
+KERNELS = {"aggregate": 0, "nlb_gemm": 1, "prep_queries": 2, "score": 3, "rescore": 4, "exact": 5,
+           "prep_gallery": 6}
 SEAM_MAX_T = 64
 SEAM_MAX_K = 32
 
@@ -69,6 +71,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_last_error.argtypes = [vp]
     lib.seam_launch_count.restype = C.c_uint64
     lib.seam_launch_count.argtypes = [vp]
+    lib.seam_profile_enable.restype = i32
+    lib.seam_profile_enable.argtypes = [vp, i32]
+    lib.seam_profile_read.restype = i32
+    lib.seam_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i32)]
     lib.seam_load_weights.restype = i32
     lib.seam_load_weights.argtypes = [vp, C.POINTER(SeamWeights), vp]
     lib.seam_load_scorer.restype = i32

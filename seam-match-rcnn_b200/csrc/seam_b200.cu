@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -31,7 +32,37 @@ struct seam_handle {
   bool have_aggregator = false;
   PFN_encodeTiled encode = nullptr;
   uint64_t launches = 0;
+  bool profiling = false;
+  struct Span { int kernel; cudaEvent_t a, b; };
+  std::vector<Span> spans;            // recorded while profiling
+  std::vector<cudaEvent_t> free_events;
   char err[512] = {0};
+};
+
+// brackets one kernel launch with CUDA events on the launching stream when profiling is on
+struct ProfileScope {
+  seam_handle* h;
+  cudaStream_t stream;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kernel;
+  static cudaEvent_t get(seam_handle* h) {
+    cudaEvent_t e = nullptr;
+    if (!h->free_events.empty()) { e = h->free_events.back(); h->free_events.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+  ProfileScope(seam_handle* h_, int kernel_, cudaStream_t s) : h(h_), stream(s), kernel(kernel_) {
+    if (h->profiling && h->spans.size() < 65536) {
+      a = get(h); b = get(h);
+      cudaEventRecord(a, stream);
+    }
+  }
+  ~ProfileScope() {
+    if (a) {
+      cudaEventRecord(b, stream);
+      h->spans.push_back({kernel, a, b});
+    }
+  }
 };
 
 static thread_local char g_create_err[256] = "";
@@ -133,6 +164,8 @@ void seam_destroy(seam_handle* h) {
   if (!h) return;
   {
     DeviceGuard guard(h->device);
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->free_events) cudaEventDestroy(e);
     cudaFree(h->fold);
   }
   delete h;
@@ -141,6 +174,34 @@ void seam_destroy(seam_handle* h) {
 const char* seam_last_error(const seam_handle* h) { return h ? h->err : g_create_err; }
 
 uint64_t seam_launch_count(const seam_handle* h) { return h ? h->launches : 0; }
+
+int seam_profile_enable(seam_handle* h, int enable) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  h->profiling = enable != 0;
+  return SEAM_OK;
+}
+
+int seam_profile_read(seam_handle* h, int kernel, double* total_ms, int* launches) {
+  if (!h || !total_ms || !launches) return SEAM_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  double tot = 0.0;
+  int n = 0;
+  std::vector<seam_handle::Span> keep;
+  for (auto& sp : h->spans) {
+    if (sp.kernel != kernel) { keep.push_back(sp); continue; }
+    SEAM_CUDA(h, cudaEventSynchronize(sp.b));
+    float ms = 0.f;
+    SEAM_CUDA(h, cudaEventElapsedTime(&ms, sp.a, sp.b));
+    tot += ms;
+    ++n;
+    h->free_events.push_back(sp.a);
+    h->free_events.push_back(sp.b);
+  }
+  h->spans.swap(keep);
+  *total_ms = tot;
+  *launches = n;
+  return SEAM_OK;
+}
 
 int seam_load_weights(seam_handle* h, const seam_weights* w, void* stream_) {
   if (!h) return SEAM_ERR_BAD_ARG;
@@ -219,8 +280,11 @@ int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const 
   p.sv = sv;
   p.att = att;
   const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
-  agg::aggregate_kernel<<<grid, agg::THREADS, sizeof(agg::Smem), stream>>>(p);
-  SEAM_LAUNCHED(h, "aggregate_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_AGGREGATE, stream);
+    agg::aggregate_kernel<<<grid, agg::THREADS, sizeof(agg::Smem), stream>>>(p);
+    SEAM_LAUNCHED(h, "aggregate_kernel");
+  }
 
   nlbgemm::Params gp;
   gp.pooled = out;
@@ -231,8 +295,11 @@ int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const 
   gp.rows = Q;
   gp.T = 0;
   dim3 ggrid((Q + nlbgemm::TM - 1) / nlbgemm::TM, 256 / nlbgemm::TN);
-  nlbgemm::nlb_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(gp);
-  SEAM_LAUNCHED(h, "nlb_gemm_simt_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_NLB_GEMM, stream);
+    nlbgemm::nlb_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(gp);
+    SEAM_LAUNCHED(h, "nlb_gemm_simt_kernel");
+  }
   return SEAM_OK;
 }
 
@@ -271,8 +338,11 @@ int seam_nlb_forward(seam_handle* h, const float* x, int B, int T, float* z, voi
   gp.rows = (int)rows;
   gp.T = T;
   dim3 ggrid((unsigned)((rows + nlbgemm::TM - 1) / nlbgemm::TM), 256 / nlbgemm::TN);
-  nlbgemm::nlb_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(gp);
-  SEAM_LAUNCHED(h, "nlb_gemm_simt_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_NLB_GEMM, stream);
+    nlbgemm::nlb_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(gp);
+    SEAM_LAUNCHED(h, "nlb_gemm_simt_kernel");
+  }
   return SEAM_OK;
 }
 
@@ -288,8 +358,11 @@ int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float
   if (G == 0) return SEAM_OK;
   if (!g || !g16 || !cg) return fail(h, SEAM_ERR_BAD_ARG, "seam_prepare_gallery: null pointer");
   if (!aligned16(g) || !aligned16(g16)) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_prepare_gallery: 16-byte alignment");
-  exact::prep_gallery_kernel<<<(G + 7) / 8, 256, 0, stream>>>(g, G, h->fold, static_cast<__half*>(g16), cg, gstat);
-  SEAM_LAUNCHED(h, "prep_gallery_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_PREP_GALLERY, stream);
+    exact::prep_gallery_kernel<<<(G + 7) / 8, 256, 0, stream>>>(g, G, h->fold, static_cast<__half*>(g16), cg, gstat);
+    SEAM_LAUNCHED(h, "prep_gallery_kernel");
+  }
   return SEAM_OK;
 }
 
@@ -413,8 +486,11 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   int32_t* counters = reinterpret_cast<int32_t*>(ws + s.off_cnt);
   int32_t* frows = reinterpret_cast<int32_t*>(ws + s.off_rows);
 
-  exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, counters);
-  SEAM_LAUNCHED(h, "prep_queries_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_PREP_QUERIES, stream);
+    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, counters);
+    SEAM_LAUNCHED(h, "prep_queries_kernel");
+  }
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -433,8 +509,11 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.cand_v = cand_v;
   sp.cand_i = cand_i;
   const int grid = s.num_items < h->num_sms ? s.num_items : h->num_sms;
-  score::score_topk_kernel<<<grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
-  SEAM_LAUNCHED(h, "score_topk_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_SCORE, stream);
+    score::score_topk_kernel<<<grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    SEAM_LAUNCHED(h, "score_topk_kernel");
+  }
 
   exact::RescoreParams rp;
   rp.q = q;
@@ -455,8 +534,11 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   rp.out_idx = out_idx;
   rp.counters = counters;
   rp.fallback_rows = frows;
-  exact::rescore_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(rp);
-  SEAM_LAUNCHED(h, "rescore_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_RESCORE, stream);
+    exact::rescore_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(rp);
+    SEAM_LAUNCHED(h, "rescore_kernel");
+  }
 
   exact::ExactParams ep;
   ep.q = q;
@@ -471,8 +553,11 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   ep.out_score = out_score;
   ep.out_margin = out_margin;
   ep.out_idx = out_idx;
-  exact::exact_topk_kernel<<<2 * h->num_sms, 256, 0, stream>>>(ep);
-  SEAM_LAUNCHED(h, "exact_topk_kernel");
+  {
+    ProfileScope prof(h, SEAM_KERNEL_EXACT, stream);
+    exact::exact_topk_kernel<<<2 * h->num_sms, 256, 0, stream>>>(ep);
+    SEAM_LAUNCHED(h, "exact_topk_kernel");
+  }
   if (stats) SEAM_CUDA(h, cudaMemcpyAsync(stats, counters, 4, cudaMemcpyDeviceToDevice, stream));
   return SEAM_OK;
 }

@@ -96,6 +96,19 @@ class SeamEngine:
     def launch_count(self) -> int:
         return int(self._lib.seam_launch_count(self._h))
 
+    def profile(self, enable: bool) -> None:
+        """Bracket the library's kernels with CUDA events (for bench.py's roofline)."""
+        self._check(self._lib.seam_profile_enable(self._h, 1 if enable else 0))
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel: (total_ms, launches)} of everything recorded since the last read."""
+        out = {}
+        for name, kid in _lib.KERNELS.items():
+            ms, n = C.c_double(), C.c_int()
+            self._check(self._lib.seam_profile_read(self._h, kid, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     # ------------------------------------------------------------------ weights
     def load_weights(self, state: Mapping[str, torch.Tensor], prefix: str = "") -> None:
         """Upload + fold the hot-path weights from a (possibly prefixed) state_dict.
