@@ -59,8 +59,8 @@ def approx_margin_ref(q, g):
 
 
 def stage_cand(e):
-    """Inspect the raw candidate lists of the tcgen05 kernel."""
-    for (Q, G) in [(64, 1000), (130, 300), (257, 5000), (1000, 20000)]:
+    """Inspect the raw per-row candidate lists of the tcgen05 kernel."""
+    for (Q, G) in [(64, 1000), (130, 300), (257, 5000), (1000, 20000), (3000, 40000)]:
         rs = np.random.RandomState(Q)
         q = torch.from_numpy(rs.randn(Q, 256).astype(np.float32))
         g = torch.from_numpy(rs.randn(G, 256).astype(np.float32))
@@ -69,22 +69,26 @@ def stage_cand(e):
         torch.cuda.synchronize()
         plan = e.score_plan(Q, G)
         ws = e._ws["score"]
-        P = plan["parts"]
-        cv = ws[plan["off_cand_v"]:plan["off_cand_v"] + Q * P * 32 * 4].view(torch.float32).view(Q, P * 32).cpu()
-        ci = ws[plan["off_cand_i"]:plan["off_cand_i"] + Q * P * 32 * 4].view(torch.int32).view(Q, P * 32).cpu()
+        RB = plan["row_capacity"]
+        buf = ws[plan["off_rowbuf"]:plan["off_rowbuf"] + Q * RB * 8].view(torch.int32).view(Q, RB, 2).cpu()
+        cnt = ws[plan["off_rowcnt"]:plan["off_rowcnt"] + Q * 4].view(torch.int32).cpu()
+        thr = ws[plan["off_thr"]:plan["off_thr"] + Q * 4].view(torch.int32).cpu()
         ref = approx_margin_ref(q, g)
-        # value check at the nominated indices
-        valid = ci >= 0
-        refv = torch.gather(ref, 1, ci.clamp(min=0).long())
-        verr = ((cv.double() - refv).abs() * valid).max().item()
-        # recall of the true approximate top-32
         top = ref.topk(min(32, G), dim=1).indices
-        miss = 0
+        miss, verr, over = 0, 0.0, 0
         for i in range(Q):
-            s = set(ci[i][valid[i]].tolist())
-            miss += sum(1 for j in top[i].tolist() if j not in s)
-        print(f"[cand] Q={Q} G={G} plan={ {k: plan[k] for k in ('query_tiles', 'gallery_tiles', 'parts', 'tiles_per_part', 'items')} } "
-              f"|cand_v - ref|max={verr:.3e} missing_from_top32={miss} fallback_rows={int(st[0])}")
+            n = int(cnt[i])
+            over += n > RB
+            n = min(n, RB)
+            vals = buf[i, :n, 0].contiguous().view(torch.float32)
+            idx = buf[i, :n, 1].long()
+            if n:
+                verr = max(verr, float((vals.double() - ref[i, idx]).abs().max()))
+            sset = set(idx.tolist())
+            miss += sum(1 for j in top[i].tolist() if j not in sset)
+        print(f"[cand] Q={Q} G={G} plan={ {k: plan[k] for k in ('query_tiles', 'gallery_tiles', 'ctas', 'ctas_per_query_tile', 'row_capacity')} } "
+              f"|cand_v - ref|max={verr:.3e} missing_from_top32={miss} list_len mean={cnt.float().mean():.1f} "
+              f"max={int(cnt.max())} overflow_rows={over} fallback_rows={int(st[0])}")
 
 
 def check_topk(sc, mg, ix, x5, k, tol=3e-5):
@@ -174,7 +178,7 @@ def stage_time(e):
             _, _, _, st = e.score_topk(q, gal, 20, return_stats=True)
             msg += (f" | prepare_gallery {t_prep * 1e3:.1f} us | score_topk {t_sc * 1e3:.1f} us = "
                     f"{Q * G / t_sc / 1e6:.2f} Gpairs/s = {Q * G * 512 / t_sc / 1e9:.1f} TFLOP/s; "
-                    f"fallback_rows={int(st[0])} plan={e.score_plan(Q, G)['parts']}x{e.score_plan(Q, G)['tiles_per_part']}")
+                    f"fallback_rows={int(st[0])} ctas_per_query_tile={e.score_plan(Q, G)['ctas_per_query_tile']}")
         print(msg)
 
 

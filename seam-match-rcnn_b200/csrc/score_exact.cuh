@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
                                                            const float* __restrict__ fold, __half* __restrict__ a16,
                                                            float* __restrict__ rq, float* __restrict__ anorm,
                                                            uint32_t* __restrict__ thr_global,
+                                                           uint32_t* __restrict__ rowcnt,
+                                                           uint32_t* __restrict__ rowflag,
                                                            int32_t* __restrict__ counters) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + warp;
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
     rq[i] = r;
     anorm[i] = sqrtf(n2);
     thr_global[i] = ptx::float_to_ordered(-INFINITY);
+    rowcnt[i] = 0;
+    rowflag[i] = 0;
     if (!(amax < FP16_MAX)) atomicExch(counters + 1, 1);
   }
 }
@@ -142,12 +146,14 @@ struct RescoreParams {
   const float* q;        // (Q,256)
   const float* g;        // (G,256)
   const float* fold;
-  const float* cand_v;   // (Q,P,32)
-  const int32_t* cand_i;
+  const uint2* rowbuf;         // (Q,RB) {approximate value, shard-local gallery row}
+  const uint32_t* rowcnt;      // (Q)
+  const uint32_t* rowflag;     // (Q)
+  const uint32_t* thr_global;  // (Q)
   const float* rq;
   const float* anorm;
   const float* gstat;
-  int Q, G, P, k, index_offset;
+  int Q, G, RB, k, index_offset;
   float* out_score;
   float* out_margin;
   int32_t* out_idx;
@@ -155,74 +161,96 @@ struct RescoreParams {
   int32_t* fallback_rows; // (Q)
 };
 
-// warp per query.  Merges the per-part candidate lists to the best 32 by approximate value,
-// re-scores them in the fp32 direct form, orders them (margin desc, index asc), writes the
-// first k, and decides whether the result is provably the exact top-k:
-//   every item NOT among the 32 has approximate value <= tau (the 32nd approximate value),
-//   hence exact margin <= tau + rq + db + eps;  the list is exact if margin_k exceeds that.
+// warp per query.
+//  1. streams the row's candidate list (everything the tensor-core pass saw at or above the
+//     row's final threshold tau) and keeps the best 32 by approximate value, sorted;
+//  2. S = candidates whose approximate value is within 2*eps of the k-th best approximate
+//     value (eps bounds |approximate - exact|): the exact top-k is a subset of S as long as S
+//     does not fill all 32 lanes (every item outside the 32 is <= the 32nd approximate value);
+//  3. re-scores S in the fp32 direct form, orders it (margin desc, index asc), writes k entries.
+// Rows that cannot be certified (S fills the window, candidates were dropped, fp16 overflow,
+// or an observed |approximate - exact| above eps) go to the exhaustive kernel.
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * 8 + warp;
   if (qi >= p.Q) return;
-  float cv;
-  uint32_t cidx;
-  {
-    const size_t o = (size_t)qi * p.P * 32;
-    cv = p.cand_v[o + lane];
-    cidx = (uint32_t)p.cand_i[o + lane];
-    for (int part = 1; part < p.P; ++part) {
-      const float nv = p.cand_v[o + part * 32 + (31 - lane)];
-      const uint32_t ni = (uint32_t)p.cand_i[o + part * 32 + (31 - lane)];
-      if (nv > cv) {
-        cv = nv;
-        cidx = ni;
+  const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
+  const uint32_t n_total = p.rowcnt[qi];
+  bool certified = !overflow && p.rowflag[qi] == 0 && n_total <= (uint32_t)p.RB;
+  const int n = (int)min(n_total, (uint32_t)p.RB);
+  const float tau = ptx::ordered_to_float(p.thr_global[qi]);
+  float cv = -INFINITY;
+  uint32_t cidx = 0xffffffffu;
+  const uint2* buf = p.rowbuf + (size_t)qi * p.RB;
+  for (int base = 0; base < n && certified; base += 32) {
+    float v = -INFINITY;
+    uint32_t id = 0xffffffffu;
+    if (base + lane < n) {
+      const uint2 e = buf[base + lane];
+      const float ev = __uint_as_float(e.x);
+      if (ev >= tau) {
+        v = ev;
+        id = e.y;
       }
-      wsort::merge32<true>(cv, cidx, lane);
     }
+    const float worst = __shfl_sync(ptx::FULL_MASK, cv, 31);
+    if (!(v > worst)) {
+      v = -INFINITY;
+      id = 0xffffffffu;
+    }
+    if (!__any_sync(ptx::FULL_MASK, v > -INFINITY)) continue;
+    wsort::sort32<false>(v, id, lane);           // ascending: cv (descending) || v is bitonic
+    if (v > cv) {
+      cv = v;
+      cidx = id;
+    }
+    wsort::merge32<true>(cv, cidx, lane);
   }
-  const float tau = __shfl_sync(ptx::FULL_MASK, cv, 31);
+  const bool valid = (int)cidx >= 0;
+  const int n_valid = __popc(__ballot_sync(ptx::FULL_MASK, valid));
+  if (n_valid < min(32, p.G)) certified = false;          // candidates are missing
+  const float a_k = __shfl_sync(ptx::FULL_MASK, cv, min(p.k, 32) - 1);
+  const float eps = EPS_COEFF * p.anorm[qi] * p.gstat[0] + 1e-5f;
+  const float cutoff = a_k - 2.f * eps;                   // a_k = -inf when fewer than k candidates
+  const bool in_S = valid && cv >= cutoff;
+  const uint32_t smask = __ballot_sync(ptx::FULL_MASK, in_S);
+  if (p.G > 32 && (smask >> 31)) certified = false;       // S fills the window
+  const int ns = __popc(smask);                           // S is a prefix of the sorted lanes
+
   const Slice qs = load_slice(p.q + (size_t)qi * 256, lane);
   const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
   const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
   const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
   float my_l0 = 0.f, my_l1 = 0.f;
-  for (int c = 0; c < 32; ++c) {
-    const int idx = __shfl_sync(ptx::FULL_MASK, (int)cidx, c);
-    if (idx < 0) continue;   // warp-uniform
-    float l0, l1;
-    pair_logits(qs, p.g + (size_t)idx * 256, w0, w1, b0, b1, lane, l0, l1);
-    if (lane == c) {
-      my_l0 = l0;
-      my_l1 = l1;
+  if (certified) {
+    for (int c = 0; c < ns; ++c) {
+      const int idx = __shfl_sync(ptx::FULL_MASK, (int)cidx, c);
+      float l0, l1;
+      pair_logits(qs, p.g + (size_t)idx * 256, w0, w1, b0, b1, lane, l0, l1);
+      if (lane == c) {
+        my_l0 = l0;
+        my_l1 = l1;
+      }
     }
   }
-  const bool valid = (int)cidx >= 0;
-  float d = valid ? my_l1 - my_l0 : -INFINITY;
-  int id = valid ? (int)cidx : INT_MAX;
-  float sc = valid ? softmax1(my_l0, my_l1) : 0.f;
+  float d = in_S ? my_l1 - my_l0 : -INFINITY;
+  int id = in_S ? (int)cidx : INT_MAX;
+  float sc = in_S ? softmax1(my_l0, my_l1) : 0.f;
+  // observed error of the tensor-core value against the bound it was trusted with
+  const float approx_d = cv + p.rq[qi] + p.fold[Fold::CONSTS + 4];
+  const bool violated = in_S && !(fabsf(d - approx_d) <= eps + 2e-5f * (1.f + fabsf(d)));
+  if (__any_sync(ptx::FULL_MASK, violated)) certified = false;
   wsort::sort32_rank(d, id, sc, lane);
   if (lane < p.k) {
     const size_t o = (size_t)qi * p.k + lane;
     const bool ok = id != INT_MAX;
-    p.out_score[o] = sc;
+    p.out_score[o] = ok ? sc : 0.f;
     p.out_margin[o] = d;
     p.out_idx[o] = ok ? id + p.index_offset : -1;
   }
-  const float dk = __shfl_sync(ptx::FULL_MASK, d, p.k - 1);
-  if (lane == 0) {
-    bool certified;
-    if (p.G <= 32) {
-      certified = true;                       // every item was a candidate
-    } else {
-      const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
-      const float db = p.fold[Fold::CONSTS + 4];
-      const float eps = EPS_COEFF * p.anorm[qi] * p.gstat[0] + 2e-5f * (1.f + fabsf(dk));
-      certified = !overflow && (dk >= tau + p.rq[qi] + db + eps);
-    }
-    if (!certified) {
-      const int slot = atomicAdd(p.counters, 1);
-      p.fallback_rows[slot] = qi;
-    }
+  if (!certified && lane == 0) {
+    const int slot = atomicAdd(p.counters, 1);
+    p.fallback_rows[slot] = qi;
   }
 }
 

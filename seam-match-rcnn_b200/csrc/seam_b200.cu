@@ -3,6 +3,7 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -367,50 +368,37 @@ int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float
 }
 
 struct ScorePlan {
-  int num_mtiles, ntiles_n, P, tpp, num_items;
-  size_t off_a16, off_rq, off_anorm, off_thr, off_cv, off_ci, off_cnt, off_rows, total;
+  int num_mtiles, ntiles_n, grid, segs_per_mtile, RB;
+  long long total_tiles;
+  size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_rowflag, off_rowbuf, off_cnt, off_rows, total;
 };
 
+// The (query tile, gallery tile) grid is linearised query-major and cut into one contiguous
+// range per CTA (score_tc.cuh).  A query tile's gallery sweep is therefore shared by at most
+// segs_per_mtile CTAs, each of which appends at most score::CAP candidates per row.
 static ScorePlan plan_score(int num_sms, int Q, int G) {
   ScorePlan s;
   s.num_mtiles = (Q + score::BM - 1) / score::BM;
   s.ntiles_n = (G + score::BN - 1) / score::BN;
   if (s.num_mtiles < 1) s.num_mtiles = 1;
   if (s.ntiles_n < 1) s.ntiles_n = 1;
-  // Split the gallery sweep of each 128-query tile into P parts so the (tile, part) items
-  // fill the SMs in whole waves; each part costs a fixed overhead (buffer warm-up + flush).
-  const double overhead_tiles = 3.0;
-  int bestP = 1;
-  double best = 1e300;
-  const int pmax = s.ntiles_n < 64 ? s.ntiles_n : 64;
-  for (int P = 1; P <= pmax; ++P) {
-    const int tpp = (s.ntiles_n + P - 1) / P;
-    if ((s.ntiles_n + tpp - 1) / tpp != P) continue;   // would leave empty parts
-    if (tpp > 256) continue;                           // 16-bit column index inside a part
-    const long items = (long)s.num_mtiles * P;
-    const long waves = (items + num_sms - 1) / num_sms;
-    const double cost = waves * (tpp + overhead_tiles);
-    if (cost < best) {
-      best = cost;
-      bestP = P;
-    }
-  }
-  s.P = bestP;
-  s.tpp = (s.ntiles_n + s.P - 1) / s.P;
-  if (s.tpp > 256) {   // enormous galleries: more parts than the search range
-    s.tpp = 256;
-    s.P = (s.ntiles_n + 255) / 256;
-  }
-  s.num_items = s.num_mtiles * s.P;
+  s.total_tiles = (long long)s.num_mtiles * s.ntiles_n;
+  s.grid = s.total_tiles < num_sms ? (int)s.total_tiles : num_sms;
+  const long long min_range = s.total_tiles / s.grid;           // shortest per-CTA range (>= 1)
+  long long segs = (s.ntiles_n + min_range - 1) / min_range + 1;
+  if (segs > s.grid) segs = s.grid;
+  s.segs_per_mtile = (int)segs;
+  s.RB = s.segs_per_mtile * score::CAP;
   size_t o = 0;
-  s.off_a16 = o;   o += align_up((size_t)Q * 256 * 2, 256);
-  s.off_rq = o;    o += align_up((size_t)Q * 4, 256);
-  s.off_anorm = o; o += align_up((size_t)Q * 4, 256);
-  s.off_thr = o;   o += align_up((size_t)Q * 4, 256);
-  s.off_cv = o;    o += align_up((size_t)Q * s.P * score::KP * 4, 256);
-  s.off_ci = o;    o += align_up((size_t)Q * s.P * score::KP * 4, 256);
-  s.off_cnt = o;   o += 256;
-  s.off_rows = o;  o += align_up((size_t)Q * 4, 256);
+  s.off_a16 = o;     o += align_up((size_t)Q * 256 * 2, 256);
+  s.off_rq = o;      o += align_up((size_t)Q * 4, 256);
+  s.off_anorm = o;   o += align_up((size_t)Q * 4, 256);
+  s.off_thr = o;     o += align_up((size_t)Q * 4, 256);
+  s.off_rowcnt = o;  o += align_up((size_t)Q * 4, 256);
+  s.off_rowflag = o; o += align_up((size_t)Q * 4, 256);
+  s.off_rowbuf = o;  o += align_up((size_t)Q * s.RB * 8, 256);
+  s.off_cnt = o;     o += 256;
+  s.off_rows = o;    o += align_up((size_t)Q * 4, 256);
   s.total = o;
   return s;
 }
@@ -424,9 +412,9 @@ size_t seam_score_workspace_bytes(const seam_handle* h, int Q, int G, int k) {
 int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out) {
   if (!h || !out || Q <= 0 || G <= 0) return SEAM_ERR_BAD_ARG;
   const ScorePlan s = plan_score(h->num_sms, Q, G);
-  const int64_t v[14] = {s.num_mtiles, s.ntiles_n, s.P, s.tpp, s.num_items, (int64_t)s.off_a16, (int64_t)s.off_rq,
-                         (int64_t)s.off_anorm, (int64_t)s.off_thr, (int64_t)s.off_cv, (int64_t)s.off_ci,
-                         (int64_t)s.off_cnt, (int64_t)s.off_rows, (int64_t)s.total};
+  const int64_t v[14] = {s.num_mtiles, s.ntiles_n, s.grid, s.segs_per_mtile, s.RB, (int64_t)s.off_a16,
+                         (int64_t)s.off_rq, (int64_t)s.off_anorm, (int64_t)s.off_thr, (int64_t)s.off_rowcnt,
+                         (int64_t)s.off_rowbuf, (int64_t)s.off_cnt, (int64_t)s.off_rows, (int64_t)s.total};
   for (int i = 0; i < 14; ++i) out[i] = v[i];
   return SEAM_OK;
 }
@@ -481,14 +469,16 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   float* rq = reinterpret_cast<float*>(ws + s.off_rq);
   float* anorm = reinterpret_cast<float*>(ws + s.off_anorm);
   uint32_t* thr = reinterpret_cast<uint32_t*>(ws + s.off_thr);
-  float* cand_v = reinterpret_cast<float*>(ws + s.off_cv);
-  int32_t* cand_i = reinterpret_cast<int32_t*>(ws + s.off_ci);
+  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(ws + s.off_rowcnt);
+  uint32_t* rowflag = reinterpret_cast<uint32_t*>(ws + s.off_rowflag);
+  uint2* rowbuf = reinterpret_cast<uint2*>(ws + s.off_rowbuf);
   int32_t* counters = reinterpret_cast<int32_t*>(ws + s.off_cnt);
   int32_t* frows = reinterpret_cast<int32_t*>(ws + s.off_rows);
 
   {
     ProfileScope prof(h, SEAM_KERNEL_PREP_QUERIES, stream);
-    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, counters);
+    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt, rowflag,
+                                                               counters);
     SEAM_LAUNCHED(h, "prep_queries_kernel");
   }
 
@@ -499,19 +489,22 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   score::Params sp;
   sp.Q = Q;
   sp.G = G;
-  sp.P = s.P;
-  sp.tiles_per_part = s.tpp;
   sp.num_mtiles = s.num_mtiles;
   sp.ntiles_n = s.ntiles_n;
-  sp.num_items = s.num_items;
+  sp.total_tiles = s.total_tiles;
+  sp.RB = s.RB;
+  {
+    const char* dm = getenv("SEAM_DEBUG_SCORE_MODE");   // developer diagnostics only
+    sp.debug_mode = dm ? atoi(dm) : 0;
+  }
   sp.cg = cg;
   sp.thr_global = thr;
-  sp.cand_v = cand_v;
-  sp.cand_i = cand_i;
-  const int grid = s.num_items < h->num_sms ? s.num_items : h->num_sms;
+  sp.rowcnt = rowcnt;
+  sp.rowflag = rowflag;
+  sp.rowbuf = rowbuf;
   {
     ProfileScope prof(h, SEAM_KERNEL_SCORE, stream);
-    score::score_topk_kernel<<<grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    score::score_topk_kernel<<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     SEAM_LAUNCHED(h, "score_topk_kernel");
   }
 
@@ -519,14 +512,16 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   rp.q = q;
   rp.g = g;
   rp.fold = h->fold;
-  rp.cand_v = cand_v;
-  rp.cand_i = cand_i;
+  rp.rowbuf = rowbuf;
+  rp.rowcnt = rowcnt;
+  rp.rowflag = rowflag;
+  rp.thr_global = thr;
   rp.rq = rq;
   rp.anorm = anorm;
   rp.gstat = gstat;
   rp.Q = Q;
   rp.G = G;
-  rp.P = s.P;
+  rp.RB = s.RB;
   rp.k = k;
   rp.index_offset = index_offset;
   rp.out_score = out_score;

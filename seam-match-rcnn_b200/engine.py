@@ -224,8 +224,8 @@ class SeamEngine:
         """Work decomposition + workspace layout seam_score_topk will use for (Q,G)."""
         out = (C.c_int64 * 14)()
         self._check(self._lib.seam_score_plan(self._h, int(Q), int(G), out))
-        names = ("query_tiles", "gallery_tiles", "parts", "tiles_per_part", "items", "off_a16", "off_rq",
-                 "off_anorm", "off_thr", "off_cand_v", "off_cand_i", "off_counters", "off_rows", "bytes")
+        names = ("query_tiles", "gallery_tiles", "ctas", "ctas_per_query_tile", "row_capacity", "off_a16",
+                 "off_rq", "off_anorm", "off_thr", "off_rowcnt", "off_rowbuf", "off_counters", "off_rows", "bytes")
         return dict(zip(names, [int(v) for v in out]))
 
     def score_dense(self, q: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
