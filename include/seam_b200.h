@@ -137,10 +137,11 @@ int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float
  *   stats      optional (4) int32: [0] = rows that took the exhaustive path               */
 size_t seam_score_workspace_bytes(const seam_handle* h, int Q, int G, int k);
 /* Introspection: how seam_score_topk decomposes a (Q,G) problem and lays out its workspace.
- * out[0] query tiles (128 rows), [1] gallery tiles (256 rows), [2] CTAs launched, [3] max
- * CTAs sharing one query tile's gallery sweep, [4] capacity RB of a row's candidate list,
- * [5..12] byte offsets of {a16, rq, anorm, thr, rowcnt, rowbuf, counters, fallback_rows} in
- * the workspace, [13] workspace bytes. */
+ * out[0] query tiles (128 rows), [1] gallery tiles (256 rows), [2] CTAs launched, [3] P = max
+ * CTAs sharing one query tile's gallery sweep (each owns 4 candidate sub-lists per row),
+ * [4] capacity of a sub-list (a power of two), [5..12] byte offsets of {a16, rq, anorm, thr,
+ * rowcnt (Q,P,4), rowbuf (Q,P,4,cap; base rounded up to a multiple of cap*8), counters,
+ * fallback_rows} in the workspace, [13] workspace bytes. */
 int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out14);
 int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const void* g16, const float* cg,
                     const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin,

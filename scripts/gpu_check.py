@@ -69,24 +69,32 @@ def stage_cand(e):
         torch.cuda.synchronize()
         plan = e.score_plan(Q, G)
         ws = e._ws["score"]
-        RB = plan["row_capacity"]
-        buf = ws[plan["off_rowbuf"]:plan["off_rowbuf"] + Q * RB * 8].view(torch.int32).view(Q, RB, 2).cpu()
-        cnt = ws[plan["off_rowcnt"]:plan["off_rowcnt"] + Q * 4].view(torch.int32).cpu()
-        thr = ws[plan["off_thr"]:plan["off_thr"] + Q * 4].view(torch.int32).cpu()
+        P, CAP = plan["ctas_per_query_tile"], plan["list_capacity"]
+        nl = P * 4
+        off = plan["off_rowbuf"]
+        off += (-(ws.data_ptr() + off)) % (CAP * 8)       # the library aligns the base to the sub-list size
+        buf = ws[off:off + Q * nl * CAP * 8].view(torch.int32).view(Q, nl, CAP, 2).cpu()
+        cnts = ws[plan["off_rowcnt"]:plan["off_rowcnt"] + Q * nl * 4].view(torch.int32).view(Q, nl).cpu()
         ref = approx_margin_ref(q, g)
         top = ref.topk(min(32, G), dim=1).indices
         miss, verr, over = 0, 0.0, 0
+        cnt = cnts.sum(1)
         for i in range(Q):
-            n = int(cnt[i])
-            over += n > RB
-            n = min(n, RB)
-            vals = buf[i, :n, 0].contiguous().view(torch.float32)
-            idx = buf[i, :n, 1].long()
-            if n:
+            vals, idx = [], []
+            for l in range(nl):
+                n = int(cnts[i, l])
+                over += n > CAP
+                n = min(n, CAP)
+                vals.append(buf[i, l, :n, 0].contiguous().view(torch.float32))
+                idx.append(buf[i, l, :n, 1].long())
+            vals, idx = torch.cat(vals), torch.cat(idx)
+            if idx.numel():
                 verr = max(verr, float((vals.double() - ref[i, idx]).abs().max()))
             sset = set(idx.tolist())
+            if len(sset) != idx.numel():
+                over += 1000000                            # duplicates would break the top-32 selection
             miss += sum(1 for j in top[i].tolist() if j not in sset)
-        print(f"[cand] Q={Q} G={G} plan={ {k: plan[k] for k in ('query_tiles', 'gallery_tiles', 'ctas', 'ctas_per_query_tile', 'row_capacity')} } "
+        print(f"[cand] Q={Q} G={G} plan={ {k: plan[k] for k in ('query_tiles', 'gallery_tiles', 'ctas', 'ctas_per_query_tile', 'list_capacity')} } "
               f"|cand_v - ref|max={verr:.3e} missing_from_top32={miss} list_len mean={cnt.float().mean():.1f} "
               f"max={int(cnt.max())} overflow_rows={over} fallback_rows={int(st[0])}")
 

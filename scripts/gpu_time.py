@@ -20,4 +20,14 @@ for it in range(10):
     if G: e.score_topk(q, gal, 20)
 torch.cuda.synchronize()
 pr = e.profile_read()
-print(f"Q={Q} T={T} G={G} mode={os.environ.get('SEAM_DEBUG_SCORE_MODE','0')}: " + ", ".join(f"{k}={v[0]/v[1]*1e3:.1f}us" for k, v in pr.items() if v[1]))
+extra = ""
+if G:
+    plan = e.score_plan(Q, G)
+    ws = e._ws["score"]
+    nl = plan["ctas_per_query_tile"] * 4
+    cn = ws[plan["off_rowcnt"]:plan["off_rowcnt"] + Q * nl * 4].view(torch.int32).view(Q, nl).float()
+    _, _, _, st = e.score_topk(q, gal, 20, return_stats=True)
+    extra = (f" | P={plan['ctas_per_query_tile']} cap={plan['list_capacity']} sublist max={int(cn.max())} "
+             f"row total mean={cn.sum(1).mean():.0f} max={int(cn.sum(1).max())} fallback_rows={int(st[0])} "
+             f"ws={plan['bytes'] / 2**20:.0f} MiB")
+print(f"Q={Q} T={T} G={G} nseed={os.environ.get('SEAM_SCORE_NSEED','-')} mode={os.environ.get('SEAM_DEBUG_SCORE_MODE','0')}: " + ", ".join(f"{k}={v[0]/v[1]*1e3:.1f}us" for k, v in pr.items() if v[1]) + extra)

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
                                                            const float* __restrict__ fold, __half* __restrict__ a16,
                                                            float* __restrict__ rq, float* __restrict__ anorm,
                                                            uint32_t* __restrict__ thr_global,
-                                                           uint32_t* __restrict__ rowcnt,
+                                                           uint32_t* __restrict__ rowcnt, int nlists,
                                                            uint32_t* __restrict__ rowflag,
                                                            int32_t* __restrict__ counters) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,11 +131,11 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   r = ptx::warp_sum(r);
   n2 = ptx::warp_sum(n2);
   amax = ptx::warp_max(amax);
+  for (int l = lane; l < nlists; l += 32) rowcnt[(size_t)i * nlists + l] = 0;
   if (lane == 0) {
     rq[i] = r;
     anorm[i] = sqrtf(n2);
     thr_global[i] = ptx::float_to_ordered(-INFINITY);
-    rowcnt[i] = 0;
     rowflag[i] = 0;
     if (!(amax < FP16_MAX)) atomicExch(counters + 1, 1);
   }
@@ -146,14 +146,14 @@ struct RescoreParams {
   const float* q;        // (Q,256)
   const float* g;        // (G,256)
   const float* fold;
-  const uint2* rowbuf;         // (Q,RB) {approximate value, shard-local gallery row}
-  const uint32_t* rowcnt;      // (Q)
+  const uint2* rowbuf;         // (Q,nlists,CAP) {approximate value, shard-local gallery row}
+  const uint32_t* rowcnt;      // (Q,nlists)
   const uint32_t* rowflag;     // (Q)
   const uint32_t* thr_global;  // (Q)
   const float* rq;
   const float* anorm;
   const float* gstat;
-  int Q, G, RB, k, index_offset;
+  int Q, G, nlists, CAP, k, index_offset;
   float* out_score;
   float* out_margin;
   int32_t* out_idx;
@@ -162,36 +162,25 @@ struct RescoreParams {
 };
 
 // warp per query.
-//  1. streams the row's candidate list (everything the tensor-core pass saw at or above the
-//     row's final threshold tau) and keeps the best 32 by approximate value, sorted;
+//  1. streams the row's candidate sub-lists (everything the tensor-core pass saw above the
+//     bound the row had at the time), compacts the entries at or above the row's final bound
+//     tau into shared memory and keeps the best 32 by approximate value, sorted;
 //  2. S = candidates whose approximate value is within 2*eps of the k-th best approximate
 //     value (eps bounds |approximate - exact|): the exact top-k is a subset of S as long as S
 //     does not fill all 32 lanes (every item outside the 32 is <= the 32nd approximate value);
 //  3. re-scores S in the fp32 direct form, orders it (margin desc, index asc), writes k entries.
 // Rows that cannot be certified (S fills the window, candidates were dropped, fp16 overflow,
 // or an observed |approximate - exact| above eps) go to the exhaustive kernel.
-__global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qi = blockIdx.x * 8 + warp;
-  if (qi >= p.Q) return;
-  const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
-  const uint32_t n_total = p.rowcnt[qi];
-  bool certified = !overflow && p.rowflag[qi] == 0 && n_total <= (uint32_t)p.RB;
-  const int n = (int)min(n_total, (uint32_t)p.RB);
-  const float tau = ptx::ordered_to_float(p.thr_global[qi]);
-  float cv = -INFINITY;
-  uint32_t cidx = 0xffffffffu;
-  const uint2* buf = p.rowbuf + (size_t)qi * p.RB;
-  for (int base = 0; base < n && certified; base += 32) {
+constexpr int RESCORE_WBUF = 512;   // compaction buffer entries per warp
+
+__device__ __forceinline__ void rescore_drain(const uint2* wb, int fill, float& cv, uint32_t& cidx, int lane) {
+  for (int base = 0; base < fill; base += 32) {
     float v = -INFINITY;
     uint32_t id = 0xffffffffu;
-    if (base + lane < n) {
-      const uint2 e = buf[base + lane];
-      const float ev = __uint_as_float(e.x);
-      if (ev >= tau) {
-        v = ev;
-        id = e.y;
-      }
+    if (base + lane < fill) {
+      const uint2 e = wb[base + lane];
+      v = __uint_as_float(e.x);
+      id = e.y;
     }
     const float worst = __shfl_sync(ptx::FULL_MASK, cv, 31);
     if (!(v > worst)) {
@@ -206,6 +195,44 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     }
     wsort::merge32<true>(cv, cidx, lane);
   }
+}
+
+__global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
+  __shared__ uint2 wbuf[8][RESCORE_WBUF];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= p.Q) return;
+  const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
+  bool certified = !overflow && p.rowflag[qi] == 0;
+  const float tau = ptx::ordered_to_float(p.thr_global[qi]);
+  float cv = -INFINITY;
+  uint32_t cidx = 0xffffffffu;
+  uint2* wb = wbuf[warp];
+  int fill = 0;
+  for (int l = 0; l < p.nlists && certified; ++l) {
+    const uint32_t n_l = p.rowcnt[(size_t)qi * p.nlists + l];
+    if (n_l > (uint32_t)p.CAP) { certified = false; break; }
+    const uint2* buf = p.rowbuf + ((size_t)qi * p.nlists + l) * p.CAP;
+    for (int base = 0; base < (int)n_l; base += 32) {
+      bool pass = false;
+      uint2 e = make_uint2(0u, 0u);
+      if (base + lane < (int)n_l) {
+        e = buf[base + lane];
+        pass = __uint_as_float(e.x) >= tau;
+      }
+      const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
+      if (pass) wb[fill + __popc(mask & ((1u << lane) - 1u))] = e;
+      fill += __popc(mask);
+      if (fill > RESCORE_WBUF - 32) {
+        __syncwarp();
+        rescore_drain(wb, fill, cv, cidx, lane);
+        fill = 0;
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
+  if (certified) rescore_drain(wb, fill, cv, cidx, lane);
   const bool valid = (int)cidx >= 0;
   const int n_valid = __popc(__ballot_sync(ptx::FULL_MASK, valid));
   if (n_valid < min(32, p.G)) certified = false;          // candidates are missing

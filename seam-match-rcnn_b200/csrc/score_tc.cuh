@@ -4,66 +4,76 @@
 //   x5 = last((q - g)^2),  score = softmax(x5)[1] = sigmoid(l1 - l0).
 // Ranking needs only d_ij = l1 - l0 = dw.(q_i - g_j)^2 + db with dw = w1 - w0, which expands to
 //   d_ij = rq_i + [ a_i . g_j + cg_j ] + db,   a_i = -2 dw (.) q_i,  rq_i = dw.q_i^2,  cg_j = dw.g_j^2.
-// The bracket is what this kernel evaluates: a_i . g_j on the tensor cores (fp16 operands,
-// fp32 accumulation in TMEM), + cg_j in the epilogue.  The (Q,G) matrix never leaves the SM:
-// each epilogue thread owns one query row, compares its accumulator columns against the
-// row's running threshold and appends survivors {value, gallery row} to a per-row buffer in
-// shared memory.  When a buffer runs full every thread of the warp prunes ITS OWN row in
-// parallel (sampled-pivot partition, no cross-lane traffic), keeping the best 32..44 entries
-// and raising the threshold.  Thresholds are shared between CTAs working on the same rows
-// through global memory (atomicMax on an order-preserving integer image of the float).
+// The bracket v_ij is what this kernel evaluates: a_i . g_j on the tensor cores (fp16 operands,
+// fp32 accumulation in TMEM), + cg_j in the epilogue.  The (Q,G) matrix never leaves the SM.
+//
+// Candidate filter (branch-free).  Every query row keeps a lower bound thr on its 32nd best v:
+// the row's columns are dealt into 32 disjoint groups (4 epilogue threads per row x 8 running
+// group maxima each, one FMNMX3 per two accumulator elements); the smallest of the 32 group
+// maxima has at least 32 distinct gallery items at or above it, hence is such a bound.  An
+// element is appended to the row's candidate list in global memory iff v > thr (one predicated
+// 8-byte store).  Nothing is ever pruned or re-ordered on the SM; the re-score kernel
+// (score_exact.cuh) selects the best 32 of a row's list and certifies the result.
+// Bounds are shared between the 4 threads of a row through shared memory after every tile and
+// between CTAs working on the same rows through global memory (atomicMax on an
+// order-preserving integer image of the float).  To warm the bound before anything is
+// appended, every segment first sweeps a few sample tiles spread over the gallery in
+// threshold-only mode.
 //
 // Work decomposition: the (query tile, gallery tile) grid is linearised query-major and cut
 // into one contiguous, equally long range per CTA; a range is processed as at most a few
-// "segments" (one query tile x a run of gallery tiles).  At the end of a segment each thread
-// appends its row's surviving candidates to that row's list in global memory.
+// "segments" (one query tile x a run of gallery tiles).
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (warp%4 selects the TMEM lane quarter).
+// Roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
+// allocator, warp 3 = stages cg tiles, warps 4..19 = epilogue (warp%4 selects the TMEM lane
+// quarter = 32 query rows, (warp-4)/4 the 64-column quarter of the tile).
 // Tile: 128 queries x 256 gallery rows, K = 256 as 4 k-blocks of 64 fp16 (128-byte swizzle).
 // The A (query) tile stays resident in shared memory for a whole segment; B (gallery)
-// k-blocks stream through a 3-stage ring; two 256-column TMEM accumulators alternate so the
-// epilogue of tile n overlaps the MMAs of tile n+1.
+// k-blocks stream through a 4-stage ring; two 256-column TMEM accumulators alternate, and an
+// epilogue warp hands its accumulator back as soon as its 64 columns sit in registers.
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <cuda.h>
 #include "sm100_ptx.cuh"
 
 namespace seam {
 namespace score {
 
-constexpr int BM = 128, BN = 256, BK = 64, NKB = 4, NSTAGE = 3;
-constexpr int CAP = 60;           // per-row buffer slots ({fp32 value, int32 gallery row} = 8 B)
-constexpr int CHUNK = 16;         // accumulator columns per tcgen05.ld
-constexpr int KEEP_LO = 32;       // a prune keeps between KEEP_LO ...
-constexpr int KEEP_HI = CAP - CHUNK;   // ... and KEEP_HI entries (room for one more chunk)
-constexpr int THREADS = 256;
+constexpr int BM = 128, BN = 256, BK = 64, NKB = 4, NSTAGE = 4;
+constexpr int CTRL_WARPS = 4, EPI_WARPS = 16;
+constexpr int THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int NQ = 4;                  // column quarters = sub-lists per (row, piece)
+constexpr int QCOLS = BN / NQ;         // 64 accumulator columns per thread per tile
+constexpr int HALF = 32;               // columns per tcgen05.ld
+constexpr int GROUPS = 8;              // running group maxima per thread (4 threads x 8 = 32 per row)
 constexpr uint32_t A_KB_BYTES = BM * BK * 2;
 constexpr uint32_t B_ST_BYTES = BN * BK * 2;
-constexpr uint32_t SLOT_STRIDE = BM * 8;   // bytes between consecutive slots of one row
 
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_B = OFF_A + NKB * A_KB_BYTES;
-constexpr uint32_t OFF_CAND = OFF_B + NSTAGE * B_ST_BYTES;
-constexpr uint32_t OFF_CG = OFF_CAND + CAP * SLOT_STRIDE;
-constexpr uint32_t OFF_BAR = OFF_CG + 2 * BN * 4;
-constexpr uint32_t NUM_BARS = 2 * NSTAGE + 2 + 4;
+constexpr uint32_t OFF_CG = OFF_B + NSTAGE * B_ST_BYTES;
+constexpr uint32_t OFF_THRX = OFF_CG + 2 * BN * 4;
+constexpr uint32_t OFF_BAR = OFF_THRX + BM * NQ * 4;
+constexpr uint32_t NUM_BARS = 2 * NSTAGE + 2 + 8;
 constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;   // + slack for manual 1024-byte alignment
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-static_assert(OFF_CAND % 16 == 0 && OFF_CG % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
-static_assert(KEEP_HI >= KEEP_LO + 8, "prune window too narrow");
+static_assert(OFF_CG % 16 == 0 && OFF_THRX % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
 struct Params {
   int Q, G, num_mtiles, ntiles_n;
   long long total_tiles;
-  int RB;                     // capacity of a row's global candidate list
-  int debug_mode;             // 0 = normal; 1 = drain only; 2 = load TMEM, no filter; 3 = filter, never append
+  int P;                      // sub-list slots per row: max CTAs sharing one query tile's sweep
+  int CAP;                    // entries per sub-list
+  int nseed;                  // threshold-only sample tiles at the start of a segment
+  int mode;                   // 0 = normal; 1 = accumulators are drained unread (MMA-only ceiling)
   const float* cg;            // (G)
   uint32_t* thr_global;       // (Q) ordered-uint image of the per-row lower bound
-  uint32_t* rowcnt;           // (Q) entries appended to rowbuf so far
+  uint32_t* rowcnt;           // (Q, P, 4) entries in each sub-list
   uint32_t* rowflag;          // (Q) nonzero: the row lost candidates, must be ranked exhaustively
-  uint2* rowbuf;              // (Q, RB) {approximate a.g + cg, shard-local gallery row}
+  uint2* rowbuf;              // (Q, P, 4, CAP) {v, shard-local gallery row}
 };
 
 // contiguous tile range of CTA b out of nb
@@ -71,101 +81,103 @@ __device__ __forceinline__ void cta_range(long long total, int nb, int b, long l
   t0 = total * b / nb;
   t1 = total * (b + 1) / nb;
 }
+// the CTA whose range contains tile t
+__device__ __forceinline__ int cta_of_tile(long long total, int nb, long long t) {
+  return (int)(((t + 1) * nb + total - 1) / total) - 1;
+}
 
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-  return v;
+// One segment = query tile m, gallery tiles [nt0, nt0 + n_main), preceded by n_seed sample tiles.
+struct Segment {
+  int m, nt0, n_main, n_seed, ntiles_n;
+  __device__ __forceinline__ int count() const { return n_seed + n_main; }
+  __device__ __forceinline__ int tile(int i) const {
+    return i < n_seed ? (int)(((long long)(2 * i + 1) * ntiles_n) / (2 * n_seed)) : nt0 + (i - n_seed);
+  }
+};
+__device__ __forceinline__ Segment segment_at(const Params& p, long long t, long long t_end, long long& next) {
+  Segment s;
+  s.m = (int)(t / p.ntiles_n);
+  s.nt0 = (int)(t - (long long)s.m * p.ntiles_n);
+  next = min(t_end, (long long)(s.m + 1) * p.ntiles_n);
+  s.n_main = (int)(next - t);
+  s.n_seed = (p.nseed > 0 && s.n_main >= 4 * p.nseed) ? p.nseed : 0;
+  s.ntiles_n = p.ntiles_n;
+  return s;
 }
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
-__device__ __forceinline__ float lds32(uint32_t addr) {
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// v = acc + cg;  if (v > cmp) { *(uint2*)wp = {v, colbase + E}; wp += 8; }   -- predicated, no branch.
+// Only the low address word advances: a sub-list never straddles a 4 GiB boundary (power-of-two
+// size, aligned to it).
+template <int E>
+__device__ __forceinline__ float add_append(uint64_t& wp, uint32_t acc, float cg, float cmp, uint32_t colbase) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 c, lo, hi;\n"
+      "add.f32 %1, %2, %3;\n"
+      "add.u32 c, %5, %6;\n"
+      "setp.gt.f32 p, %1, %4;\n"
+      "@p st.global.v2.b32 [%0], {%1, c};\n"
+      "mov.b64 {lo, hi}, %0;\n"
+      "@p add.u32 lo, lo, 8;\n"
+      "mov.b64 %0, {lo, hi};\n"
+      "}\n"
+      : "+l"(wp), "=f"(v)
+      : "f"(__uint_as_float(acc)), "f"(cg), "f"(cmp), "r"(colbase), "n"(E)
+      : "memory");
   return v;
 }
 
-#define SEAM_CE(a, b)               \
-  {                                 \
-    const float hi_ = fmaxf(a, b);  \
-    const float lo_ = fminf(a, b);  \
-    a = hi_;                        \
-    b = lo_;                        \
-  }
+// ties the destination registers of an in-flight tcgen05.ld to the wait so the compiler
+// cannot read them before the data has landed
+__device__ __forceinline__ void tmem_ld_wait_x32(uint32_t (&a)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]),
+                 "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]),
+                 "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]),
+                 "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
+               :
+               : "memory");
+}
 
-// Thread-local prune of one row's buffer (slots [0,cnt) at base + s*SLOT_STRIDE).
-// Picks a pivot from 8 sorted samples such that between KEEP_LO and KEEP_HI entries exceed it,
-// compacts those to the front, returns the new count and raises thr to the pivot.
-// Returns false when no pivot works (massive ties): the row is then compacted lossily and must
-// be flagged for the exhaustive path by the caller.
-__device__ __forceinline__ bool prune_row_local(uint32_t base, int& cnt, float& thr) {
-  float s0, s1, s2, s3, s4, s5, s6, s7;
-  s0 = lds32(base + ((0 * cnt) >> 3) * SLOT_STRIDE);
-  s1 = lds32(base + ((1 * cnt) >> 3) * SLOT_STRIDE);
-  s2 = lds32(base + ((2 * cnt) >> 3) * SLOT_STRIDE);
-  s3 = lds32(base + ((3 * cnt) >> 3) * SLOT_STRIDE);
-  s4 = lds32(base + ((4 * cnt) >> 3) * SLOT_STRIDE);
-  s5 = lds32(base + ((5 * cnt) >> 3) * SLOT_STRIDE);
-  s6 = lds32(base + ((6 * cnt) >> 3) * SLOT_STRIDE);
-  s7 = lds32(base + ((7 * cnt) >> 3) * SLOT_STRIDE);
-  // 19-comparator sorting network, descending
-  SEAM_CE(s0, s1) SEAM_CE(s2, s3) SEAM_CE(s4, s5) SEAM_CE(s6, s7)
-  SEAM_CE(s0, s2) SEAM_CE(s1, s3) SEAM_CE(s4, s6) SEAM_CE(s5, s7)
-  SEAM_CE(s1, s2) SEAM_CE(s5, s6) SEAM_CE(s0, s4) SEAM_CE(s3, s7)
-  SEAM_CE(s1, s5) SEAM_CE(s2, s6)
-  SEAM_CE(s1, s4) SEAM_CE(s3, s6)
-  SEAM_CE(s2, s4) SEAM_CE(s3, s5)
-  SEAM_CE(s3, s4)
-  // counts above four candidate pivots, and the row maximum, in one pass
-  int c4 = 0, c5 = 0, c6 = 0, c7 = 0;
-  float vmax = -INFINITY;
-  for (int s = 0; s < cnt; ++s) {
-    const float v = lds32(base + s * SLOT_STRIDE);
-    c4 += v > s4;
-    c5 += v > s5;
-    c6 += v > s6;
-    c7 += v > s7;
-    vmax = fmaxf(vmax, v);
+// 16 accumulator columns of one row (r[OFF..OFF+16)): + cg, append what beats cmp, fold into
+// the 8 group maxima (two columns per group and call)
+template <int OFF, int... E>
+__device__ __forceinline__ void filter16_impl(const uint32_t (&r)[32], const float* cgp, float (&gm)[GROUPS],
+                                              uint64_t& wp, float cmp, uint32_t col0,
+                                              std::integer_sequence<int, E...>) {
+  float cgv[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const float4 g4 = *reinterpret_cast<const float4*>(cgp + OFF + c4 * 4);
+    cgv[c4 * 4 + 0] = g4.x;
+    cgv[c4 * 4 + 1] = g4.y;
+    cgv[c4 * 4 + 2] = g4.z;
+    cgv[c4 * 4 + 3] = g4.w;
   }
-  // bracket the window [KEEP_LO, KEEP_HI]: pl has too many entries above it, ph too few
-  float pl = -INFINITY, ph = vmax, pivot = vmax;
-  bool found = false;
-#define SEAM_TRY(P, C)                                   \
-  if (!found) {                                          \
-    if ((C) > KEEP_HI) pl = fmaxf(pl, (P));              \
-    else if ((C) >= KEEP_LO) { pivot = (P); found = true; } \
-    else ph = fminf(ph, (P));                            \
-  }
-  SEAM_TRY(s7, c7) SEAM_TRY(s6, c6) SEAM_TRY(s5, c5) SEAM_TRY(s4, c4)
-#undef SEAM_TRY
-  // no sample landed in the window: bisect between the bracketing values
-  for (int iter = 0; iter < 12 && !found; ++iter) {
-    const float mid = pl == -INFINITY ? ph - fmaxf(1e-3f, fabsf(ph) * 1e-3f) * (float)(1 << iter) : 0.5f * (pl + ph);
-    if (!(mid > pl) || !(mid < ph)) break;               // no representable value in between (ties)
-    int c = 0;
-    for (int s = 0; s < cnt; ++s) c += lds32(base + s * SLOT_STRIDE) > mid;
-    if (c > KEEP_HI) pl = mid;
-    else if (c >= KEEP_LO) { pivot = mid; found = true; }
-    else ph = mid;
-  }
-  bool ok = found;
-  if (!found) pivot = ph;                                // ties: keep fewer than KEEP_LO, row becomes lossy
-  int w = 0;
-  for (int s = 0; s < cnt; ++s) {
-    const uint2 e = lds64(base + s * SLOT_STRIDE);
-    if (__uint_as_float(e.x) > pivot) {
-      if (w < KEEP_HI) sts64(base + w * SLOT_STRIDE, e.x, e.y);
-      ++w;
-    }
-  }
-  if (w > KEEP_HI) {   // could not make room without dropping entries above the pivot
-    w = KEEP_HI;
-    ok = false;
-  }
-  cnt = w;
-  thr = fmaxf(thr, pivot);
-  return ok;
+  float v[16];
+  ((v[E] = add_append<OFF + E>(wp, r[OFF + E], cgv[E], cmp, col0)), ...);
+#pragma unroll
+  for (int g = 0; g < GROUPS; ++g) gm[g] = max3(gm[g], v[g], v[g + 8]);
+}
+// 32 accumulator columns of one row
+__device__ __forceinline__ void filter32(const uint32_t (&r)[32], const float* cgp, float (&gm)[GROUPS], uint64_t& wp,
+                                         float cmp, uint32_t col0) {
+  filter16_impl<0>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
+  filter16_impl<16>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -176,17 +188,21 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   uint8_t* sA = smem + OFF_A;
   uint8_t* sB = smem + OFF_B;
-  float* cg_s = reinterpret_cast<float*>(smem + OFF_CG);
+  float* cg_s = reinterpret_cast<float*>(smem + OFF_CG);        // [2][BN]
+  float* thr_x = reinterpret_cast<float*>(smem + OFF_THRX);     // [BM][NQ] group-minimum of each thread
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
   uint64_t* empty = bars + NSTAGE;          // [NSTAGE]  MMA -> TMA
   uint64_t* a_full = bars + 2 * NSTAGE;     // A tile landed
   uint64_t* a_empty = a_full + 1;           // all MMAs of the segment retired
-  uint64_t* t_full = a_empty + 1;           // [2] accumulator ready
-  uint64_t* t_empty = t_full + 2;           // [2] accumulator drained
+  uint64_t* t_full = a_empty + 1;           // [2] accumulator ready            (MMA -> epilogue)
+  uint64_t* t_empty = t_full + 2;           // [2] accumulator read out         (epilogue -> MMA)
+  uint64_t* cg_full = t_empty + 2;          // [2] cg tile staged               (warp 3 -> epilogue)
+  uint64_t* cg_empty = cg_full + 2;         // [2] cg tile consumed             (epilogue -> warp 3)
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(ptx::FULL_MASK, tid >> 5, 0);   // provably warp-uniform role dispatch
 
   if (tid == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -199,7 +215,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&t_full[i], 1);
-      ptx::mbar_init(&t_empty[i], 4);
+      ptx::mbar_init(&t_empty[i], EPI_WARPS);
+      ptx::mbar_init(&cg_full[i], 1);
+      ptx::mbar_init(&cg_empty[i], EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
@@ -219,16 +237,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ================================================================= TMA producer
     if (lane == 0) {
       uint32_t stage = 0, sphase = 0, iphase = 0;
-      long long t = t_begin;
+      long long t = t_begin, next;
       while (t < t_end) {
-        const int m = (int)(t / p.ntiles_n);
-        const int nt0 = (int)(t - (long long)m * p.ntiles_n);
-        const long long seg_end = min(t_end, (long long)(m + 1) * p.ntiles_n);
-        const int nt1 = nt0 + (int)(seg_end - t);
+        const Segment sg = segment_at(p, t, t_end, next);
         ptx::mbar_wait(a_empty, iphase ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, NKB * A_KB_BYTES);
-        for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, m * BM);
-        for (int nt = nt0; nt < nt1; ++nt) {
+        for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, sg.m * BM);
+        const int n = sg.count();
+        for (int i = 0; i < n; ++i) {
+          const int nt = sg.tile(i);
           for (int kb = 0; kb < NKB; ++kb) {
             ptx::mbar_wait(&empty[stage], sphase ^ 1);
             ptx::mbar_arrive_expect_tx(&full[stage], B_ST_BYTES);
@@ -240,7 +257,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         iphase ^= 1;
-        t = seg_end;
+        t = next;
       }
     }
   } else if (warp == 1) {
@@ -249,13 +266,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t idesc = ptx::umma_idesc(0 /*fp16*/, BM, BN);
       const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
       uint32_t stage = 0, sphase = 0, iphase = 0, acc = 0, aphase = 0;
-      long long t = t_begin;
+      long long t = t_begin, next;
       while (t < t_end) {
-        const int m = (int)(t / p.ntiles_n);
-        const long long seg_end = min(t_end, (long long)(m + 1) * p.ntiles_n);
-        const int ntiles = (int)(seg_end - t);
+        const Segment sg = segment_at(p, t, t_end, next);
+        const int n = sg.count();
         ptx::mbar_wait(a_full, iphase);
-        for (int it = 0; it < ntiles; ++it) {
+        for (int i = 0; i < n; ++i) {
           ptx::mbar_wait(&t_empty[acc], aphase ^ 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
@@ -282,129 +298,127 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         ptx::umma_commit(a_empty);
         iphase ^= 1;
-        t = seg_end;
+        t = next;
       }
     }
-  } else if (warp >= 4) {
-    // ================================================================= epilogue
-    const int ew = warp - 4;                 // TMEM lane quarter
-    const int R = ew * 32 + lane;            // row within the CTA tile
-    const int etid = tid - 128;
-    const uint32_t cand_base = ptx::smem_u32(smem + OFF_CAND) + R * 8;
+  } else if (warp == 3) {
+    // ================================================================= cg stager
     uint32_t acc = 0, aphase = 0;
-    long long t = t_begin;
+    long long t = t_begin, next;
     while (t < t_end) {
-      const int m = (int)(t / p.ntiles_n);
-      const int nt0 = (int)(t - (long long)m * p.ntiles_n);
-      const long long seg_end = min(t_end, (long long)(m + 1) * p.ntiles_n);
-      const int nt1 = nt0 + (int)(seg_end - t);
-      const int grow = m * BM + R;
-      const bool row_ok = grow < p.Q;
-      float thr = (row_ok && p.debug_mode != 3) ? -INFINITY : INFINITY;
-      uint32_t wp = cand_base;               // address of the next free slot
-      bool lossy = false;
-      for (int nt = nt0; nt < nt1; ++nt) {
-        // stage cg for this tile (-inf beyond G so padded columns never qualify)
-        {
-          float* dst = cg_s + acc * BN;
-          const int j0 = nt * BN + etid, j1 = j0 + 128;
-          dst[etid] = j0 < p.G ? __ldg(p.cg + j0) : -INFINITY;
-          dst[etid + 128] = j1 < p.G ? __ldg(p.cg + j1) : -INFINITY;
+      const Segment sg = segment_at(p, t, t_end, next);
+      const int n = sg.count();
+      for (int i = 0; i < n; ++i) {
+        const int j0 = sg.tile(i) * BN + lane * 8;
+        float c[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c[e] = (j0 + e < p.G) ? __ldg(p.cg + j0 + e) : -INFINITY;   // padded columns never qualify
+        ptx::mbar_wait(&cg_empty[acc], aphase ^ 1);
+        float* dst = cg_s + acc * BN + lane * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(c[0], c[1], c[2], c[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(c[4], c[5], c[6], c[7]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&cg_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          aphase ^= 1;
         }
-        if (row_ok) thr = fmaxf(thr, ptx::ordered_to_float(__ldcg(p.thr_global + grow)));
-        ptx::named_bar_sync(1, 128);
+      }
+      t = next;
+    }
+  } else if (warp >= CTRL_WARPS) {
+    // ================================================================= epilogue
+    const int ew = warp - CTRL_WARPS;
+    const int lq = ew & 3;                   // TMEM lane quarter (must equal warp % 4)
+    const int cq = ew >> 2;                  // column quarter of the tile
+    const int R = lq * 32 + lane;            // row within the CTA tile
+    uint32_t acc = 0, aphase = 0;
+    long long t = t_begin, next;
+    while (t < t_end) {
+      const Segment sg = segment_at(p, t, t_end, next);
+      const int n = sg.count();
+      const int grow = sg.m * BM + R;
+      const bool row_ok = grow < p.Q;
+      const int piece = blockIdx.x - cta_of_tile(p.total_tiles, gridDim.x, (long long)sg.m * p.ntiles_n);
+      const bool slot_ok = row_ok && piece >= 0 && piece < p.P;
+      const size_t li = slot_ok ? ((size_t)grow * p.P + piece) * NQ + cq : 0;
+      const uint64_t wp_begin = reinterpret_cast<uint64_t>(p.rowbuf + li * (size_t)p.CAP);
+      const uint64_t wp_limit = wp_begin + (uint64_t)(p.CAP - QCOLS) * 8;   // room for one more tile's 64 columns
+      uint64_t wp = wp_begin;
+      float thr = row_ok ? ptx::ordered_to_float(__ldcg(p.thr_global + grow)) : INFINITY;
+      bool closed = !slot_ok;                // the list takes no (more) entries
+      bool lossy = row_ok && !slot_ok;
+      float gm[GROUPS];
+#pragma unroll
+      for (int g = 0; g < GROUPS; ++g) gm[g] = -INFINITY;
+      thr_x[R * NQ + cq] = -INFINITY;
+      ptx::named_bar_sync(1, EPI_THREADS);   // previous segment's bounds are gone before anyone reads
+
+      for (int i = 0; i < n; ++i) {
+        const int nt = sg.tile(i);
         ptx::mbar_wait(&t_full[acc], aphase);
         ptx::tc_fence_after();
-        if (p.debug_mode == 1 || p.debug_mode == 2) {
-          if (p.debug_mode == 2) {
-            const uint32_t ta = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
-            uint32_t rr[CHUNK];
-            uint32_t accum = 0;
-            for (int ch = 0; ch < BN / CHUNK; ++ch) {
-              ptx::tmem_ld_x16(ta + ch * CHUNK, rr);
-              ptx::tmem_ld_wait_x16(rr);
-#pragma unroll
-              for (int e = 0; e < CHUNK; ++e) accum ^= rr[e];
-            }
-            if (accum == 0x12345678u) p.rowflag[0] = 1;
-          }
+        if (p.mode == 1) {
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+          if (lane == 0) {
+            ptx::mbar_wait(&cg_full[acc], aphase);
+            ptx::mbar_arrive(&t_empty[acc]);
+            ptx::mbar_arrive(&cg_empty[acc]);
+          }
           if (++acc == 2) {
             acc = 0;
             aphase ^= 1;
           }
           continue;
         }
-        const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
-        const float* cgt = cg_s + acc * BN;
-        const int col0 = nt * BN;
-        uint32_t r[CHUNK];
-        ptx::tmem_ld_x16(taddr, r);
-#pragma unroll 1
-        for (int ch = 0; ch < BN / CHUNK; ++ch) {
-          ptx::tmem_ld_wait_x16(r);
-          float x[CHUNK];
-#pragma unroll
-          for (int e = 0; e < CHUNK; ++e) x[e] = __uint_as_float(r[e]);
-          if (ch + 1 < BN / CHUNK) ptx::tmem_ld_x16(taddr + (ch + 1) * CHUNK, r);   // prefetch next chunk
-#pragma unroll
-          for (int c4 = 0; c4 < CHUNK / 4; ++c4) {
-            const float4 g4 = *reinterpret_cast<const float4*>(cgt + ch * CHUNK + c4 * 4);
-            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float v = x[c4 * 4 + e] + gg[e];
-              if (v > thr) {
-                sts64(wp, __float_as_uint(v), (uint32_t)(col0 + ch * CHUNK + c4 * 4 + e));
-                wp += SLOT_STRIDE;
-              }
-            }
-          }
-          const bool need = (wp - cand_base) > (uint32_t)KEEP_HI * SLOT_STRIDE;
-          if (__any_sync(ptx::FULL_MASK, need)) {
-            int cnt = (int)((wp - cand_base) / SLOT_STRIDE);
-            if (cnt > KEEP_HI - 4) {          // rows close to the limit prune together
-              const float before = thr;
-              if (!prune_row_local(cand_base, cnt, thr)) lossy = true;
-              wp = cand_base + cnt * SLOT_STRIDE;
-              if (thr > before && !lossy) atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
-            }
-            __syncwarp();
-          }
+        const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + acc * BN + cq * QCOLS;
+        if (i >= sg.n_seed && wp > wp_limit && !closed) {   // no room for another tile: stop appending,
+          closed = true;                                    // the row goes to the exhaustive path
+          lossy = true;
         }
-        // accumulator drained: hand it back to the MMA warp
+        const float cmp = (closed || i < sg.n_seed) ? INFINITY : thr;
+        const float* cgp = cg_s + acc * BN + cq * QCOLS;
+        const uint32_t col0 = (uint32_t)(nt * BN + cq * QCOLS);
+        uint32_t r[32];
+        ptx::tmem_ld_x32(taddr, r);
+        ptx::mbar_wait(&cg_full[acc], aphase);
+        tmem_ld_wait_x32(r);
+        filter32(r, cgp, gm, wp, cmp, col0);
+        ptx::tmem_ld_x32(taddr + HALF, r);
+        tmem_ld_wait_x32(r);
+        // this warp's accumulator columns have all been read: hand the TMEM slot back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+        filter32(r, cgp + HALF, gm, wp, cmp, col0 + HALF);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&cg_empty[acc]);
+        // share the bound: 32 disjoint groups per row = 4 threads x 8 maxima
+        {
+          const float m0 = min3(gm[0], gm[1], gm[2]);
+          const float m1 = min3(gm[3], gm[4], gm[5]);
+          const float mine = min3(m0, m1, fminf(gm[6], gm[7]));
+          thr_x[R * NQ + cq] = mine;
+          const float4 o = *reinterpret_cast<const float4*>(thr_x + R * NQ);   // partners' values may be stale: still valid
+          thr = fmaxf(thr, fminf(fminf(o.x, o.y), fminf(o.z, o.w)));
+        }
+        if ((i & 7) == 7 && row_ok) {        // exchange with the other CTAs sweeping these rows
+          const uint32_t old = atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
+          thr = fmaxf(thr, ptx::ordered_to_float(old));
+        }
         if (++acc == 2) {
           acc = 0;
           aphase ^= 1;
         }
       }
-      // ---- flush: append this row's surviving candidates to its global list
+      // ---- segment end: publish the list length, the bound and the loss flag
       if (row_ok) {
-        const int cnt = (int)((wp - cand_base) / SLOT_STRIDE);
-        const float tg = ptx::ordered_to_float(__ldcg(p.thr_global + grow));
-        int npass = 0;
-        for (int s = 0; s < cnt; ++s) npass += lds32(cand_base + s * SLOT_STRIDE) >= tg;
+        if (slot_ok) p.rowcnt[li] = (uint32_t)((wp - wp_begin) >> 3);
         if (lossy) atomicOr(p.rowflag + grow, 1u);
-        if (npass > 0) {
-          uint32_t slot = atomicAdd(p.rowcnt + grow, (uint32_t)npass);
-          uint2* dst = p.rowbuf + (size_t)grow * p.RB;
-          for (int s = 0; s < cnt; ++s) {
-            const uint2 e = lds64(cand_base + s * SLOT_STRIDE);
-            if (__uint_as_float(e.x) >= tg) {
-              if (slot < (uint32_t)p.RB) dst[slot] = e;
-              ++slot;
-            }
-          }
-          if (slot > (uint32_t)p.RB) atomicOr(p.rowflag + grow, 2u);
-        }
+        atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
       }
-      __syncwarp();
-      t = seg_end;
+      t = next;
     }
   }
 

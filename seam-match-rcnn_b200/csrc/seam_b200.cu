@@ -1,6 +1,7 @@
 // C ABI of the B200-native SEAM Match-RCNN retrieval hot path (see include/seam_b200.h).
 // Host-side argument checking, workspace carving, tensor-map encoding and kernel launches.
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -368,14 +369,20 @@ int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float
 }
 
 struct ScorePlan {
-  int num_mtiles, ntiles_n, grid, segs_per_mtile, RB;
+  int num_mtiles, ntiles_n, grid, P, CAP, nseed;
   long long total_tiles;
   size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_rowflag, off_rowbuf, off_cnt, off_rows, total;
 };
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 // The (query tile, gallery tile) grid is linearised query-major and cut into one contiguous
-// range per CTA (score_tc.cuh).  A query tile's gallery sweep is therefore shared by at most
-// segs_per_mtile CTAs, each of which appends at most score::CAP candidates per row.
+// range per CTA (score_tc.cuh).  A query tile's gallery sweep is therefore shared by at most P
+// CTAs ("pieces"); each piece owns 4 candidate sub-lists per row (one per epilogue thread of
+// the row) of CAP entries, CAP >= 3 times the expected number of appends.
 static ScorePlan plan_score(int num_sms, int Q, int G) {
   ScorePlan s;
   s.num_mtiles = (Q + score::BM - 1) / score::BM;
@@ -385,18 +392,42 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
   s.total_tiles = (long long)s.num_mtiles * s.ntiles_n;
   s.grid = s.total_tiles < num_sms ? (int)s.total_tiles : num_sms;
   const long long min_range = s.total_tiles / s.grid;           // shortest per-CTA range (>= 1)
+  const long long max_range = (s.total_tiles + s.grid - 1) / s.grid;
   long long segs = (s.ntiles_n + min_range - 1) / min_range + 1;
   if (segs > s.grid) segs = s.grid;
-  s.segs_per_mtile = (int)segs;
-  s.RB = s.segs_per_mtile * score::CAP;
+  s.P = (int)segs;
+  s.nseed = env_int("SEAM_SCORE_NSEED", 2);
+  // expected appends of one epilogue thread over a piece of T tiles (64 columns each): with a
+  // cold bound the first tile is appended whole and tile t adds ~32/t (about 130 items sit above
+  // a row's 32-group bound, a quarter of them in this thread's columns); seeded pieces start at
+  // the rate of tile nseed+1.
+  // Segments shorter than 4*nseed tiles run unseeded and may append whole tiles.
+  const double T = (double)(max_range < s.ntiles_n ? max_range : s.ntiles_n);
+  double need;
+  if (s.nseed > 0) {
+    const double short_tiles = T < 4.0 * s.nseed - 1.0 ? T : 4.0 * s.nseed - 1.0;
+    need = short_tiles * score::QCOLS;
+    if (T >= 4.0 * s.nseed) {
+      const double seeded = 3.0 * (16.0 + 32.0 * log((T + s.nseed) / s.nseed));
+      if (seeded > need) need = seeded;
+    }
+  } else {
+    need = 3.0 * (64.0 + 32.0 * log(T));
+  }
+  if (need > T * score::QCOLS) need = T * score::QCOLS;      // a thread cannot append more than it sees
+  need += score::QCOLS;                                      // a list closes one tile before it is full
+  int cap = 2 * score::QCOLS;                                // power of two: a sub-list is aligned to its size
+  while (cap < (int)need && cap < 8192) cap *= 2;
+  s.CAP = cap;
+  const size_t nlists = (size_t)s.P * score::NQ;
   size_t o = 0;
   s.off_a16 = o;     o += align_up((size_t)Q * 256 * 2, 256);
   s.off_rq = o;      o += align_up((size_t)Q * 4, 256);
   s.off_anorm = o;   o += align_up((size_t)Q * 4, 256);
   s.off_thr = o;     o += align_up((size_t)Q * 4, 256);
-  s.off_rowcnt = o;  o += align_up((size_t)Q * 4, 256);
+  s.off_rowcnt = o;  o += align_up((size_t)Q * nlists * 4, 256);
   s.off_rowflag = o; o += align_up((size_t)Q * 4, 256);
-  s.off_rowbuf = o;  o += align_up((size_t)Q * s.RB * 8, 256);
+  s.off_rowbuf = o;  o += align_up((size_t)Q * nlists * s.CAP * 8 + (size_t)s.CAP * 8, 256);   // + slack to align the base
   s.off_cnt = o;     o += 256;
   s.off_rows = o;    o += align_up((size_t)Q * 4, 256);
   s.total = o;
@@ -412,7 +443,7 @@ size_t seam_score_workspace_bytes(const seam_handle* h, int Q, int G, int k) {
 int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out) {
   if (!h || !out || Q <= 0 || G <= 0) return SEAM_ERR_BAD_ARG;
   const ScorePlan s = plan_score(h->num_sms, Q, G);
-  const int64_t v[14] = {s.num_mtiles, s.ntiles_n, s.grid, s.segs_per_mtile, s.RB, (int64_t)s.off_a16,
+  const int64_t v[14] = {s.num_mtiles, s.ntiles_n, s.grid, s.P, s.CAP, (int64_t)s.off_a16,
                          (int64_t)s.off_rq, (int64_t)s.off_anorm, (int64_t)s.off_thr, (int64_t)s.off_rowcnt,
                          (int64_t)s.off_rowbuf, (int64_t)s.off_cnt, (int64_t)s.off_rows, (int64_t)s.total};
   for (int i = 0; i < 14; ++i) out[i] = v[i];
@@ -471,14 +502,16 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   uint32_t* thr = reinterpret_cast<uint32_t*>(ws + s.off_thr);
   uint32_t* rowcnt = reinterpret_cast<uint32_t*>(ws + s.off_rowcnt);
   uint32_t* rowflag = reinterpret_cast<uint32_t*>(ws + s.off_rowflag);
-  uint2* rowbuf = reinterpret_cast<uint2*>(ws + s.off_rowbuf);
+  // sub-lists are aligned to their (power-of-two) size so that none straddles a 4 GiB boundary
+  uint2* rowbuf = reinterpret_cast<uint2*>(
+      align_up(reinterpret_cast<uintptr_t>(ws + s.off_rowbuf), (size_t)s.CAP * 8));
   int32_t* counters = reinterpret_cast<int32_t*>(ws + s.off_cnt);
   int32_t* frows = reinterpret_cast<int32_t*>(ws + s.off_rows);
 
   {
     ProfileScope prof(h, SEAM_KERNEL_PREP_QUERIES, stream);
-    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt, rowflag,
-                                                               counters);
+    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt,
+                                                               s.P * score::NQ, rowflag, counters);
     SEAM_LAUNCHED(h, "prep_queries_kernel");
   }
 
@@ -492,11 +525,10 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.num_mtiles = s.num_mtiles;
   sp.ntiles_n = s.ntiles_n;
   sp.total_tiles = s.total_tiles;
-  sp.RB = s.RB;
-  {
-    const char* dm = getenv("SEAM_DEBUG_SCORE_MODE");   // developer diagnostics only
-    sp.debug_mode = dm ? atoi(dm) : 0;
-  }
+  sp.P = s.P;
+  sp.CAP = s.CAP;
+  sp.nseed = s.nseed;
+  sp.mode = env_int("SEAM_DEBUG_SCORE_MODE", 0);   // developer diagnostics only
   sp.cg = cg;
   sp.thr_global = thr;
   sp.rowcnt = rowcnt;
@@ -521,7 +553,8 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   rp.gstat = gstat;
   rp.Q = Q;
   rp.G = G;
-  rp.RB = s.RB;
+  rp.nlists = s.P * score::NQ;
+  rp.CAP = s.CAP;
   rp.k = k;
   rp.index_offset = index_offset;
   rp.out_score = out_score;

@@ -224,7 +224,7 @@ class SeamEngine:
         """Work decomposition + workspace layout seam_score_topk will use for (Q,G)."""
         out = (C.c_int64 * 14)()
         self._check(self._lib.seam_score_plan(self._h, int(Q), int(G), out))
-        names = ("query_tiles", "gallery_tiles", "ctas", "ctas_per_query_tile", "row_capacity", "off_a16",
+        names = ("query_tiles", "gallery_tiles", "ctas", "ctas_per_query_tile", "list_capacity", "off_a16",
                  "off_rq", "off_anorm", "off_thr", "off_rowcnt", "off_rowbuf", "off_counters", "off_rows", "bytes")
         return dict(zip(names, [int(v) for v in out]))
 
