@@ -13,7 +13,8 @@
 //      q_j = (1/T) sum_t p_t relu(a_t+b_j),
 //   C  pooled = sum_t p_t x_t and r = sum_j q_j x_j (one thread per channel).
 // Each frame is read from HBM exactly once.  The per-track 256->256 map M r (the NLB's
-// g/W projections applied to r) is batched over tracks by K1b (nlb_gemm.cuh).
+// g/W projections applied to r) is batched over tracks by K1b (nlb_tc.cuh).  This kernel serves
+// tracks longer than 16 frames; shorter ones take the warp-per-track kernel (aggregate_warp.cuh).
 #pragma once
 #include <cstdint>
 #include "fold.cuh"
@@ -37,9 +38,9 @@ struct Params {
   int Tmax, Q, NT, rows, num_tiles;
   long long frame_stride, track_stride;   // floats
   const float* fold;
-  float* pooled;   // (Q,256)  sum_t p_t x_t
-  float* R;        // (Q,256)  sum_j q_j x_j
-  float* sv;       // (Q,2)    {sum_j q_j, nlb_active}
+  float* pooled;   // (Q,256)  pooled' = sum_t p_t x_t + (sum_j q_j) W_W b_g + [T>1] b_W
+  float* r_hi;     // (Q,256)  r = sum_j q_j x_j split into tf32-exact halves (nlb_tc.cuh)
+  float* r_lo;     // (Q,256)
   float* att;      // (Q,Tmax) or null
 };
 
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_kernel(const Params p) {
       // ---- C: weighted sums, one thread per channel
       {
         const int c = ctid;
+        const float wbg = fold[Fold::WBG + c], bW = fold[Fold::BW + c];
         for (int n = 0; n < NT; ++n) {
           const int track = tile * NT + n;
           if (track >= p.Q) break;
@@ -258,12 +260,11 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_kernel(const Params p) {
             r = fmaf(qt, xv, r);
             qs += qt;
           }
+          if (ln > 1) pooled += fmaf(qs, wbg, bW);
+          const float hi = __uint_as_float(__float_as_uint(r) & 0xffffe000u);   // tf32-exact split
           p.pooled[(size_t)track * D + c] = pooled;
-          p.R[(size_t)track * D + c] = r;
-          if (c == 0) {
-            p.sv[2 * track] = qs;
-            p.sv[2 * track + 1] = ln > 1 ? 1.f : 0.f;
-          }
+          p.r_hi[(size_t)track * D + c] = hi;
+          p.r_lo[(size_t)track * D + c] = r - hi;
         }
       }
       __syncwarp();

@@ -1,0 +1,308 @@
+// K1a (short tracks): streaming temporal aggregation, one WARP per track.
+//
+// Replaces the per-track Python loop of TemporalAggregationNLB.forward's seq-branch,
+// models/match_head.py:133-154, and the block it calls, models/nlb.py:66-101, for tracks of up
+// to TR frames (TR = 4, 10 or 16; longer tracks use the CTA-per-tile kernel in aggregate.cuh).
+//
+// Every warp owns a private ring of SLOTS track buffers in shared memory and fills it itself:
+// lane t issues one 1 KB bulk async copy (cp.async.bulk + mbarrier complete_tx) for frame t of
+// the track SLOTS-1 iterations ahead; padded frames of ragged tracks are never read.  There is
+// no block-wide synchronisation anywhere: warps drift apart freely, which keeps ~100 KB of
+// loads in flight per SM.  A track's frames are pulled into registers once (8 floats per lane
+// and frame) and used for both passes:
+//   A  four length-256 dots per frame (a, d, b, c of DESIGN.md "K1 algebra"), reduced with
+//      transposing butterflies (40 shuffles for 40 values at T = 10),
+//   B  lane t: s_t = d_t + c_s + (1/T) sum_j relu(a_t+b_j) c_j ; p = softmax_t(s) ;
+//      q_j = (1/T) sum_t p_t relu(a_t+b_j),
+//   C  pooled = sum_t p_t x_t and r = sum_j q_j x_j (8 channels per lane).
+// Outputs per track: pooled' = pooled + (sum_j q_j) W_W b_g + [T>1] b_W, and r split into
+// tf32-exact halves r_hi + r_lo for the tensor-core product M r of K1b (nlb_tc.cuh).
+#pragma once
+#include <cstdint>
+#include "fold.cuh"
+#include "sm100_ptx.cuh"
+
+namespace seam {
+namespace aggw {
+
+constexpr int D = 256;
+
+struct Params {
+  const float* seq;
+  const uint8_t* mask;     // (Q, 1+Tmax) or null
+  const int32_t* lens;     // (Q) or null
+  int Tmax, Q;
+  long long frame_stride, track_stride;   // floats
+  const float* fold;
+  float* pooled;   // (Q,256)  pooled'
+  float* r_hi;     // (Q,256)
+  float* r_lo;     // (Q,256)
+  float* att;      // (Q,Tmax) or null
+};
+
+template <int TR>
+struct Cfg;
+template <>
+struct Cfg<4> { static constexpr int NW = 16, SLOTS = 3; };
+template <>
+struct Cfg<10> { static constexpr int NW = 10, SLOTS = 2; };
+template <>
+struct Cfg<16> { static constexpr int NW = 7, SLOTS = 2; };
+
+template <int TR>
+constexpr size_t smem_bytes() {
+  return (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * TR * D * 4      // track buffers
+         + (size_t)Cfg<TR>::NW * 64 * 4                          // per-warp scalars (a,p,p/b,q/c per frame)
+         + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * 8              // mbarriers
+         + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * 4;             // track lengths
+}
+
+// Transposing butterfly: N per-lane values (N = 8, 16, 32) are summed over the 32 lanes; lane l
+// returns the total of v[l % N].
+template <int N>
+__device__ __forceinline__ float treduce(float (&v)[N], int lane) {
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(ptx::FULL_MASK, send, half);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int o = N; o < 32; o <<= 1) r += __shfl_xor_sync(ptx::FULL_MASK, r, o);
+  return r;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& x) {
+  acc.x = fmaf(s, x.x, acc.x);
+  acc.y = fmaf(s, x.y, acc.y);
+  acc.z = fmaf(s, x.z, acc.z);
+  acc.w = fmaf(s, x.w, acc.w);
+}
+// tf32-exact split: hi keeps the 10 explicit mantissa bits the tensor core reads, lo the rest
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+template <int TR>
+__global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(const Params p) {
+  constexpr int NW = Cfg<TR>::NW, SLOTS = Cfg<TR>::SLOTS;
+  constexpr int NV = TR * 4;                       // scalars per track
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xbuf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * SLOTS * TR * D;
+  float* scal = reinterpret_cast<float*>(smem_raw) + (size_t)NW * SLOTS * TR * D + warp * 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NW * SLOTS * TR * D * 4 + (size_t)NW * 64 * 4) +
+                   warp * SLOTS;
+  int* slot_len = reinterpret_cast<int*>(smem_raw + (size_t)NW * SLOTS * TR * D * 4 + (size_t)NW * 64 * 4 +
+                                         (size_t)NW * SLOTS * 8) + warp * SLOTS;
+  const int Tmax = p.Tmax;
+
+  if (lane == 0) {
+    for (int i = 0; i < SLOTS; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+
+  const long long stride = (long long)gridDim.x * NW;
+  const long long first = (long long)blockIdx.x * NW + warp;
+
+  // start the copies of one track into a slot; returns nothing, the length goes to slot_len
+  auto issue = [&](long long track, int slot) {
+    int len = 0;
+    if (track < p.Q) {
+      if (p.lens) {
+        len = p.lens[track];
+      } else if (p.mask) {
+        // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
+        const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
+        const bool set = lane <= Tmax && m[lane] != 0;
+        const uint32_t b = __ballot_sync(ptx::FULL_MASK, set);
+        const int end = b ? __ffs(b) - 1 : 1 + Tmax;
+        len = end - 1;
+      } else {
+        len = Tmax;
+      }
+      len = max(0, min(len, Tmax));
+    }
+    if (lane == 0) {
+      slot_len[slot] = len;
+      if (len > 0) ptx::mbar_arrive_expect_tx(&bars[slot], (uint32_t)len * (D * 4));
+      else ptx::mbar_arrive(&bars[slot]);
+    }
+    __syncwarp();
+    if (lane < len) {
+      const float* src = p.seq + (long long)(lane + 1) * p.frame_stride + track * p.track_stride;
+      ptx::bulk_load_1d(xbuf + ((size_t)slot * TR + lane) * D, src, D * 4, &bars[slot]);
+    }
+  };
+
+  // folded vectors at this lane's two float4 positions
+  const float* fold = p.fold;
+  const float4 ut0 = *reinterpret_cast<const float4*>(fold + Fold::U_THETA + 4 * lane);
+  const float4 ut1 = *reinterpret_cast<const float4*>(fold + Fold::U_THETA + 128 + 4 * lane);
+  const float4 up0 = *reinterpret_cast<const float4*>(fold + Fold::U_PHI + 4 * lane);
+  const float4 up1 = *reinterpret_cast<const float4*>(fold + Fold::U_PHI + 128 + 4 * lane);
+  const float4 ug0 = *reinterpret_cast<const float4*>(fold + Fold::U_G + 4 * lane);
+  const float4 ug1 = *reinterpret_cast<const float4*>(fold + Fold::U_G + 128 + 4 * lane);
+  const float4 wa0 = *reinterpret_cast<const float4*>(fold + Fold::W_A + 4 * lane);
+  const float4 wa1 = *reinterpret_cast<const float4*>(fold + Fold::W_A + 128 + 4 * lane);
+  const float c_s = fold[Fold::CONSTS + 3];
+  // scalar layout per frame: [a, d, b, c]; constants c_theta, 0, c_phi, c_g
+  const int comp = lane & 3;
+  const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
+                       : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
+
+#pragma unroll 1
+  for (int i = 0; i < SLOTS - 1; ++i) issue(first + i * stride, i);
+
+  int it = 0;
+#pragma unroll 1
+  for (long long track = first; track < p.Q; track += stride, ++it) {
+    const int slot = it % SLOTS;
+    const uint32_t phase = (uint32_t)(it / SLOTS) & 1u;
+    __syncwarp();                                    // every lane is done with the slot being refilled
+    issue(track + (long long)(SLOTS - 1) * stride, (it + SLOTS - 1) % SLOTS);
+    ptx::mbar_wait(&bars[slot], phase);
+    const int len = slot_len[slot];
+    const float* xs = xbuf + (size_t)slot * TR * D;
+
+    // ---- frames -> registers, four dots per frame
+    float4 x0[TR], x1[TR];
+    constexpr int N1 = NV <= 16 ? 16 : 32;                       // first butterfly: frames 0..7
+    constexpr int N2 = NV <= 32 ? 1 : (NV - 32 <= 8 ? 8 : 32);    // second butterfly: frames 8..
+    float acc[N1], acc2[N2];
+#pragma unroll
+    for (int i = 0; i < N1; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < N2; ++i) acc2[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < TR; ++t) {
+      if (t < len) {
+        x0[t] = *reinterpret_cast<const float4*>(xs + t * D + 4 * lane);
+        x1[t] = *reinterpret_cast<const float4*>(xs + t * D + 128 + 4 * lane);
+      } else {
+        x0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[t] = x0[t];
+      }
+      const float va = dot4(x0[t], ut0) + dot4(x1[t], ut1);
+      const float vd = dot4(x0[t], wa0) + dot4(x1[t], wa1);
+      const float vb = dot4(x0[t], up0) + dot4(x1[t], up1);
+      const float vc = dot4(x0[t], ug0) + dot4(x1[t], ug1);
+      if (4 * t < 32) {
+        acc[4 * t + 0] = va;
+        acc[4 * t + 1] = vd;
+        acc[4 * t + 2] = vb;
+        acc[4 * t + 3] = vc;
+      } else {
+        acc2[4 * t - 32 + 0] = va;
+        acc2[4 * t - 32 + 1] = vd;
+        acc2[4 * t - 32 + 2] = vb;
+        acc2[4 * t - 32 + 3] = vc;
+      }
+    }
+    if constexpr (NV <= 16) {
+      const float tot = treduce<16>(acc, lane);
+      if (lane < 16) scal[lane] = tot + my_const;
+    } else {
+      const float tot = treduce<32>(acc, lane);
+      scal[lane] = tot + my_const;
+      if constexpr (NV > 32) {
+        if constexpr (N2 == 8) {
+          const float tot2 = treduce<8>(acc2, lane);
+          if (lane < 8) scal[32 + lane] = tot2 + my_const;
+        } else {
+          const float tot2 = treduce<32>(acc2, lane);
+          scal[32 + lane] = tot2 + my_const;
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- attention over the track's frames (lane = frame)
+    const bool valid = lane < len;
+    const float inv_len = len > 0 ? 1.f / (float)len : 0.f;
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) sc = *reinterpret_cast<const float4*>(scal + 4 * lane);   // a, d, b, c of my frame
+    float sum = 0.f;
+    if (len > 1) {
+      for (int j = 0; j < len; ++j) {
+        const float2 bc = *reinterpret_cast<const float2*>(scal + 4 * j + 2);
+        sum = fmaf(fmaxf(sc.x + bc.x, 0.f) * inv_len, bc.y, sum);
+      }
+    }
+    const float s_t = valid ? sc.y + sum + c_s : -INFINITY;
+    const float m = ptx::warp_max(s_t);
+    const float e_t = valid ? expf(s_t - m) : 0.f;
+    const float z = ptx::warp_sum(e_t);
+    const float p_t = valid ? e_t / z : 0.f;
+    __syncwarp();                                    // all lanes have read b, c, d
+    if (lane < TR) {
+      scal[4 * lane + 1] = p_t;
+      scal[4 * lane + 2] = p_t;
+    }
+    __syncwarp();
+    float q_j = 0.f;
+    if (len > 1 && valid) {
+      for (int t = 0; t < len; ++t) {
+        const float2 ap = *reinterpret_cast<const float2*>(scal + 4 * t);
+        q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
+      }
+    }
+    if (lane < TR) scal[4 * lane + 3] = q_j;
+    const float qsum = ptx::warp_sum(q_j);
+    if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
+    __syncwarp();
+
+    // ---- weighted sums over frames, 8 channels per lane
+    float4 po0 = make_float4(0.f, 0.f, 0.f, 0.f), po1 = po0, r0 = po0, r1 = po0;
+#pragma unroll
+    for (int t = 0; t < TR; ++t) {
+      if (t < len) {
+        const float2 pq = *reinterpret_cast<const float2*>(scal + 4 * t + 2);
+        fma4(po0, pq.x, x0[t]);
+        fma4(po1, pq.x, x1[t]);
+        fma4(r0, pq.y, x0[t]);
+        fma4(r1, pq.y, x1[t]);
+      }
+    }
+    if (len > 1) {
+      const float4 wbg0 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 4 * lane);
+      const float4 wbg1 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 128 + 4 * lane);
+      const float4 bw0 = *reinterpret_cast<const float4*>(fold + Fold::BW + 4 * lane);
+      const float4 bw1 = *reinterpret_cast<const float4*>(fold + Fold::BW + 128 + 4 * lane);
+      po0.x += fmaf(qsum, wbg0.x, bw0.x);
+      po0.y += fmaf(qsum, wbg0.y, bw0.y);
+      po0.z += fmaf(qsum, wbg0.z, bw0.z);
+      po0.w += fmaf(qsum, wbg0.w, bw0.w);
+      po1.x += fmaf(qsum, wbg1.x, bw1.x);
+      po1.y += fmaf(qsum, wbg1.y, bw1.y);
+      po1.z += fmaf(qsum, wbg1.z, bw1.z);
+      po1.w += fmaf(qsum, wbg1.w, bw1.w);
+    }
+    float4 h0, l0, h1, l1;
+    split_tf32(r0, h0, l0);
+    split_tf32(r1, h1, l1);
+    const size_t o = (size_t)track * D + 4 * lane;
+    *reinterpret_cast<float4*>(p.pooled + o) = po0;
+    *reinterpret_cast<float4*>(p.pooled + o + 128) = po1;
+    *reinterpret_cast<float4*>(p.r_hi + o) = h0;
+    *reinterpret_cast<float4*>(p.r_hi + o + 128) = h1;
+    *reinterpret_cast<float4*>(p.r_lo + o) = l0;
+    *reinterpret_cast<float4*>(p.r_lo + o + 128) = l1;
+  }
+}
+
+}  // namespace aggw
+}  // namespace seam

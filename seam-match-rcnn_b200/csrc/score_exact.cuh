@@ -209,25 +209,46 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   uint32_t cidx = 0xffffffffu;
   uint2* wb = wbuf[warp];
   int fill = 0;
-  for (int l = 0; l < p.nlists && certified; ++l) {
-    const uint32_t n_l = p.rowcnt[(size_t)qi * p.nlists + l];
-    if (n_l > (uint32_t)p.CAP) { certified = false; break; }
-    const uint2* buf = p.rowbuf + ((size_t)qi * p.nlists + l) * p.CAP;
-    for (int base = 0; base < (int)n_l; base += 32) {
-      bool pass = false;
-      uint2 e = make_uint2(0u, 0u);
-      if (base + lane < (int)n_l) {
-        e = buf[base + lane];
-        pass = __uint_as_float(e.x) >= tau;
-      }
-      const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
-      if (pass) wb[fill + __popc(mask & ((1u << lane) - 1u))] = e;
-      fill += __popc(mask);
-      if (fill > RESCORE_WBUF - 32) {
-        __syncwarp();
-        rescore_drain(wb, fill, cv, cidx, lane);
-        fill = 0;
-        __syncwarp();
+  // sub-lists are short (tens of entries): sweep them 32 at a time (lane = sub-list) and keep
+  // four loads per lane in flight -- the kernel is latency-bound, not bandwidth-bound
+  for (int l0 = 0; l0 < p.nlists && certified; l0 += 32) {
+    const int my_l = l0 + lane;
+    uint32_t my_n = my_l < p.nlists ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
+    if (__any_sync(ptx::FULL_MASK, my_n > (uint32_t)p.CAP)) {
+      certified = false;
+      break;
+    }
+    const int nl = min(32, p.nlists - l0);
+    for (int j0 = 0; j0 < nl; j0 += 2) {
+      const int nA = (int)__shfl_sync(ptx::FULL_MASK, my_n, j0);
+      const int nB = (int)__shfl_sync(ptx::FULL_MASK, my_n, min(j0 + 1, 31));
+      const uint2* bufA = p.rowbuf + ((size_t)qi * p.nlists + l0 + j0) * p.CAP;
+      const uint2* bufB = bufA + p.CAP;
+      const int nBv = j0 + 1 < nl ? nB : 0;
+      for (int base = 0; base < max(nA, nBv); base += 64) {
+        uint2 e[4];
+        bool ok[4];
+        ok[0] = base + lane < nA;
+        ok[1] = base + 32 + lane < nA;
+        ok[2] = base + lane < nBv;
+        ok[3] = base + 32 + lane < nBv;
+        e[0] = ok[0] ? __ldcs(bufA + base + lane) : make_uint2(0u, 0u);
+        e[1] = ok[1] ? __ldcs(bufA + base + 32 + lane) : make_uint2(0u, 0u);
+        e[2] = ok[2] ? __ldcs(bufB + base + lane) : make_uint2(0u, 0u);
+        e[3] = ok[3] ? __ldcs(bufB + base + 32 + lane) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool pass = ok[u] && __uint_as_float(e[u].x) >= tau;
+          const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
+          if (pass) wb[fill + __popc(mask & ((1u << lane) - 1u))] = e[u];
+          fill += __popc(mask);
+        }
+        if (fill > RESCORE_WBUF - 128) {
+          __syncwarp();
+          rescore_drain(wb, fill, cv, cidx, lane);
+          fill = 0;
+          __syncwarp();
+        }
       }
     }
   }
@@ -250,13 +271,24 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
   float my_l0 = 0.f, my_l1 = 0.f;
   if (certified) {
-    for (int c = 0; c < ns; ++c) {
-      const int idx = __shfl_sync(ptx::FULL_MASK, (int)cidx, c);
-      float l0, l1;
-      pair_logits(qs, p.g + (size_t)idx * 256, w0, w1, b0, b1, lane, l0, l1);
-      if (lane == c) {
-        my_l0 = l0;
-        my_l1 = l1;
+    // four candidates per step: their 1 KB gallery rows are fetched together
+    for (int c0 = 0; c0 < ns; c0 += 4) {
+      Slice gs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = __shfl_sync(ptx::FULL_MASK, (int)cidx, min(c0 + u, ns - 1));
+        gs[u] = load_slice(p.g + (size_t)idx * 256, lane);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float p0, p1;
+        sqdiff_dot2(qs, gs[u], w0, w1, p0, p1);
+        const float l0 = ptx::warp_sum(p0) + b0;
+        const float l1 = ptx::warp_sum(p1) + b1;
+        if (lane == c0 + u) {
+          my_l0 = l0;
+          my_l1 = l1;
+        }
       }
     }
   }

@@ -15,8 +15,10 @@
 
 #include "../../include/seam_b200.h"
 #include "aggregate.cuh"
+#include "aggregate_warp.cuh"
 #include "fold.cuh"
 #include "nlb_gemm.cuh"
+#include "nlb_tc.cuh"
 #include "score_exact.cuh"
 #include "score_tc.cuh"
 
@@ -109,6 +111,26 @@ struct DeviceGuard {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+static int encode_map_f32_rows(seam_handle* h, CUtensorMap* map, const void* base, int rows, int box_rows) {
+  const cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {256 * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};   // 32 fp32 = one 128-byte swizzle row
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, SEAM_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+  return SEAM_OK;
+}
+
+template <int TR>
+static void launch_aggregate_warp(const aggw::Params& p, int num_sms, cudaStream_t stream) {
+  constexpr int NW = aggw::Cfg<TR>::NW;
+  const int want = (p.Q + NW - 1) / NW;
+  const int grid = want < num_sms ? want : num_sms;
+  aggw::aggregate_warp_kernel<TR><<<grid, NW * 32, aggw::smem_bytes<TR>(), stream>>>(p);
+}
+
 extern "C" {
 
 int seam_abi_version(void) { return 1; }
@@ -151,6 +173,13 @@ int seam_create(seam_handle** out, int device) {
   cudaFuncSetAttribute(agg::aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(agg::Smem));
   cudaFuncSetAttribute(score::score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)score::SMEM_BYTES);
+  cudaFuncSetAttribute(aggw::aggregate_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggw::smem_bytes<4>());
+  cudaFuncSetAttribute(aggw::aggregate_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggw::smem_bytes<10>());
+  cudaFuncSetAttribute(aggw::aggregate_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggw::smem_bytes<16>());
+  cudaFuncSetAttribute(nlbtc::nlb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nlbtc::SMEM_BYTES);
   cudaFuncSetAttribute(nlbgemm::nlb_full_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)((SEAM_MAX_T * 257 + 2 * SEAM_MAX_T) * sizeof(float)));
   if ((e = cudaGetLastError()) != cudaSuccess) {
@@ -236,7 +265,7 @@ int seam_load_scorer(seam_handle* h, const float* last_w, const float* last_b, v
 // ------------------------------------------------------------------------------ aggregation
 size_t seam_aggregate_workspace_bytes(int Q) {
   if (Q <= 0) return 256;
-  return align_up((size_t)Q * 256 * 4, 256) + align_up((size_t)Q * 2 * 4, 256);
+  return 3 * align_up((size_t)Q * 256 * 4, 256);   // pooled', r_hi, r_lo
 }
 
 int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const int32_t* lens, int Tmax, int Q,
@@ -257,50 +286,77 @@ int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const 
   if (!seq || !workspace) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: null pointer");
   if (!aligned16(seq) || !aligned16(out) || (frame_stride & 3) || (track_stride & 3))
     return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: seq/out must be 16-byte aligned, strides multiples of 4");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: workspace must be 256-byte aligned");
   if (workspace_bytes < seam_aggregate_workspace_bytes(Q))
     return fail(h, SEAM_ERR_STATE, "seam_aggregate: workspace too small (%zu < %zu)", workspace_bytes,
                 seam_aggregate_workspace_bytes(Q));
-  float* R = static_cast<float*>(workspace);
-  float* sv = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up((size_t)Q * 256 * 4, 256));
+  const size_t plane = align_up((size_t)Q * 256 * 4, 256);
+  float* pooled = static_cast<float*>(workspace);
+  float* r_hi = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plane);
+  float* r_lo = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * plane);
 
-  agg::Params p;
-  p.seq = seq;
-  p.mask = mask;
-  p.lens = lens;
-  p.Tmax = Tmax;
-  p.Q = Q;
-  p.NT = agg::ROWS_MAX / Tmax;
-  if (p.NT > agg::MAX_NT) p.NT = agg::MAX_NT;
-  if (p.NT < 1) p.NT = 1;
-  p.rows = p.NT * Tmax;
-  p.num_tiles = (Q + p.NT - 1) / p.NT;
-  p.frame_stride = frame_stride;
-  p.track_stride = track_stride;
-  p.fold = h->fold;
-  p.pooled = out;
-  p.R = R;
-  p.sv = sv;
-  p.att = att;
-  const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
   {
     ProfileScope prof(h, SEAM_KERNEL_AGGREGATE, stream);
-    agg::aggregate_kernel<<<grid, agg::THREADS, sizeof(agg::Smem), stream>>>(p);
-    SEAM_LAUNCHED(h, "aggregate_kernel");
+    if (Tmax <= 16) {
+      aggw::Params p;
+      p.seq = seq;
+      p.mask = mask;
+      p.lens = lens;
+      p.Tmax = Tmax;
+      p.Q = Q;
+      p.frame_stride = frame_stride;
+      p.track_stride = track_stride;
+      p.fold = h->fold;
+      p.pooled = pooled;
+      p.r_hi = r_hi;
+      p.r_lo = r_lo;
+      p.att = att;
+      if (Tmax <= 4) launch_aggregate_warp<4>(p, h->num_sms, stream);
+      else if (Tmax <= 10) launch_aggregate_warp<10>(p, h->num_sms, stream);
+      else launch_aggregate_warp<16>(p, h->num_sms, stream);
+      SEAM_LAUNCHED(h, "aggregate_warp_kernel");
+    } else {
+      agg::Params p;
+      p.seq = seq;
+      p.mask = mask;
+      p.lens = lens;
+      p.Tmax = Tmax;
+      p.Q = Q;
+      p.NT = agg::ROWS_MAX / Tmax;
+      if (p.NT > agg::MAX_NT) p.NT = agg::MAX_NT;
+      if (p.NT < 1) p.NT = 1;
+      p.rows = p.NT * Tmax;
+      p.num_tiles = (Q + p.NT - 1) / p.NT;
+      p.frame_stride = frame_stride;
+      p.track_stride = track_stride;
+      p.fold = h->fold;
+      p.pooled = pooled;
+      p.r_hi = r_hi;
+      p.r_lo = r_lo;
+      p.att = att;
+      const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
+      agg::aggregate_kernel<<<grid, agg::THREADS, sizeof(agg::Smem), stream>>>(p);
+      SEAM_LAUNCHED(h, "aggregate_kernel");
+    }
   }
 
-  nlbgemm::Params gp;
-  gp.pooled = out;
-  gp.R = R;
-  gp.sv = sv;
-  gp.fold = h->fold;
+  // K1b: out = pooled' + (r_hi + r_lo) M^T on the tensor cores
+  CUtensorMap tmRh, tmRl, tmMh, tmMl;
+  int rc;
+  if ((rc = encode_map_f32_rows(h, &tmRh, r_hi, Q, nlbtc::BM)) != SEAM_OK) return rc;
+  if ((rc = encode_map_f32_rows(h, &tmRl, r_lo, Q, nlbtc::BM)) != SEAM_OK) return rc;
+  if ((rc = encode_map_f32_rows(h, &tmMh, h->fold + Fold::M_HI, 256, nlbtc::BN)) != SEAM_OK) return rc;
+  if ((rc = encode_map_f32_rows(h, &tmMl, h->fold + Fold::M_LO, 256, nlbtc::BN)) != SEAM_OK) return rc;
+  nlbtc::Params gp;
+  gp.pooled = pooled;
   gp.out = out;
   gp.rows = Q;
-  gp.T = 0;
-  dim3 ggrid((Q + nlbgemm::TM - 1) / nlbgemm::TM, 256 / nlbgemm::TN);
   {
     ProfileScope prof(h, SEAM_KERNEL_NLB_GEMM, stream);
-    nlbgemm::nlb_gemm_simt_kernel<<<ggrid, 256, 0, stream>>>(gp);
-    SEAM_LAUNCHED(h, "nlb_gemm_simt_kernel");
+    nlbtc::nlb_tc_kernel<<<(Q + nlbtc::BM - 1) / nlbtc::BM, nlbtc::THREADS, nlbtc::SMEM_BYTES, stream>>>(
+        tmRh, tmRl, tmMh, tmMl, gp);
+    SEAM_LAUNCHED(h, "nlb_tc_kernel");
   }
   return SEAM_OK;
 }
