@@ -137,6 +137,7 @@ def test_evaluate_aggregated_report(model, weights):
     gal = so.synth_gallery(G, 2, None)
     target = torch.arange(Q) * 2
     eng = model._engine_for(torch.device(DEV))
+    model._sync_weights(eng)                     # an earlier test left the engine with nlb=False weights
     rep = pkg.evaluate_aggregated(eng, seq.to(DEV), mask.to(DEV), gal.to(DEV), target)
     x5 = so.pair_logits(qref, gal, weights)
     ranks = so.rank_of_target(x5, target)
