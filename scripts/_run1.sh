@@ -1,1 +1,3 @@
-python -m pytest tests -m gpu -q > gpurun_out/r4_pytest.log 2>&1; tail -15 gpurun_out/r4_pytest.log
+python scripts/gpu_check.py cand topk 2>&1 | grep -v "^\[topk\] Q" | tail -8
+python scripts/gpu_time.py 15000 10 15000 2>&1 | tail -1
+python scripts/gpu_time.py 10000 10 125000 2>&1 | tail -1
