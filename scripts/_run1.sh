@@ -1,3 +1,3 @@
-python scripts/gpu_check.py cand topk 2>&1 | grep -v "^\[topk\] Q" | tail -8
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
 python scripts/gpu_time.py 15000 10 15000 2>&1 | tail -1
 python scripts/gpu_time.py 10000 10 125000 2>&1 | tail -1

@@ -57,25 +57,7 @@ constexpr size_t smem_bytes() {
          + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * 4;             // track lengths
 }
 
-// Transposing butterfly: N per-lane values (N = 8, 16, 32) are summed over the 32 lanes; lane l
-// returns the total of v[l % N].
-template <int N>
-__device__ __forceinline__ float treduce(float (&v)[N], int lane) {
-#pragma unroll
-  for (int half = N / 2; half >= 1; half >>= 1) {
-    const bool upper = (lane & half) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = upper ? v[i] : v[i + half];
-      const float keep = upper ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(ptx::FULL_MASK, send, half);
-    }
-  }
-  float r = v[0];
-#pragma unroll
-  for (int o = N; o < 32; o <<= 1) r += __shfl_xor_sync(ptx::FULL_MASK, r, o);
-  return r;
-}
+using ptx::treduce;
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));

@@ -57,8 +57,8 @@ __device__ __forceinline__ void pair_logits(const Slice& q, const float* grow, c
   const Slice g = load_slice(grow, lane);
   float p0, p1;
   sqdiff_dot2(q, g, w0, w1, p0, p1);
-  l0 = ptx::warp_sum(p0) + b0;
-  l1 = ptx::warp_sum(p1) + b1;
+  l0 = ptx::warp_sum_b(p0) + b0;   // same association as the butterfly in rescore_kernel
+  l1 = ptx::warp_sum_b(p1) + b1;
 }
 
 // ---------------------------------------------------------------- gallery preparation
@@ -171,30 +171,30 @@ struct RescoreParams {
 //  3. re-scores S in the fp32 direct form, orders it (margin desc, index asc), writes k entries.
 // Rows that cannot be certified (S fills the window, candidates were dropped, fp16 overflow,
 // or an observed |approximate - exact| above eps) go to the exhaustive kernel.
-constexpr int RESCORE_WBUF = 512;   // compaction buffer entries per warp
+constexpr int RESCORE_WBUF = 288;   // compaction buffer entries per warp (256 new + < 32 kept)
 
-__device__ __forceinline__ void rescore_drain(const uint2* wb, int fill, float& cv, uint32_t& cidx, int lane) {
-  for (int base = 0; base < fill; base += 32) {
-    float v = -INFINITY;
-    uint32_t id = 0xffffffffu;
-    if (base + lane < fill) {
-      const uint2 e = wb[base + lane];
-      v = __uint_as_float(e.x);
-      id = e.y;
-    }
-    const float worst = __shfl_sync(ptx::FULL_MASK, cv, 31);
-    if (!(v > worst)) {
-      v = -INFINITY;
-      id = 0xffffffffu;
-    }
-    if (!__any_sync(ptx::FULL_MASK, v > -INFINITY)) continue;
-    wsort::sort32<false>(v, id, lane);           // ascending: cv (descending) || v is bitonic
-    if (v > cv) {
-      cv = v;
-      cidx = id;
-    }
-    wsort::merge32<true>(cv, cidx, lane);
+// merge the entries wb[begin, begin+32) (fewer at the tail) into the running sorted best-32
+__device__ __forceinline__ void rescore_merge32(const uint2* wb, int begin, int end, float& cv, uint32_t& cidx,
+                                                int lane) {
+  float v = -INFINITY;
+  uint32_t id = 0xffffffffu;
+  if (begin + lane < end) {
+    const uint2 e = wb[begin + lane];
+    v = __uint_as_float(e.x);
+    id = e.y;
   }
+  const float worst = __shfl_sync(ptx::FULL_MASK, cv, 31);
+  if (!(v > worst)) {
+    v = -INFINITY;
+    id = 0xffffffffu;
+  }
+  if (!__any_sync(ptx::FULL_MASK, v > -INFINITY)) return;
+  wsort::sort32<false>(v, id, lane);           // ascending: cv (descending) || v is bitonic
+  if (v > cv) {
+    cv = v;
+    cidx = id;
+  }
+  wsort::merge32<true>(cv, cidx, lane);
 }
 
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
@@ -209,8 +209,13 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   uint32_t cidx = 0xffffffffu;
   uint2* wb = wbuf[warp];
   int fill = 0;
-  // sub-lists are short (tens of entries): sweep them 32 at a time (lane = sub-list) and keep
-  // four loads per lane in flight -- the kernel is latency-bound, not bandwidth-bound
+  // Streaming top-32 with a running cut: an entry is compacted into shared memory only if it
+  // beats both the row's final bound tau and the 32nd best seen so far, and the buffer is merged
+  // into the sorted best-32 (one bitonic sort + merge) whenever 32 such entries have gathered --
+  // about 32 (1 + ln(n/32)) entries ever get that far.  Sub-lists are short (tens of entries):
+  // they are swept four at a time with eight loads per lane in flight.
+  float cut = tau;                                 // max(tau, 32nd best so far); entries equal to tau pass
+  bool cut_strict = false;
   for (int l0 = 0; l0 < p.nlists && certified; l0 += 32) {
     const int my_l = l0 + lane;
     uint32_t my_n = my_l < p.nlists ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
@@ -219,41 +224,53 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
       break;
     }
     const int nl = min(32, p.nlists - l0);
-    for (int j0 = 0; j0 < nl; j0 += 2) {
-      const int nA = (int)__shfl_sync(ptx::FULL_MASK, my_n, j0);
-      const int nB = (int)__shfl_sync(ptx::FULL_MASK, my_n, min(j0 + 1, 31));
-      const uint2* bufA = p.rowbuf + ((size_t)qi * p.nlists + l0 + j0) * p.CAP;
-      const uint2* bufB = bufA + p.CAP;
-      const int nBv = j0 + 1 < nl ? nB : 0;
-      for (int base = 0; base < max(nA, nBv); base += 64) {
-        uint2 e[4];
-        bool ok[4];
-        ok[0] = base + lane < nA;
-        ok[1] = base + 32 + lane < nA;
-        ok[2] = base + lane < nBv;
-        ok[3] = base + 32 + lane < nBv;
-        e[0] = ok[0] ? __ldcs(bufA + base + lane) : make_uint2(0u, 0u);
-        e[1] = ok[1] ? __ldcs(bufA + base + 32 + lane) : make_uint2(0u, 0u);
-        e[2] = ok[2] ? __ldcs(bufB + base + lane) : make_uint2(0u, 0u);
-        e[3] = ok[3] ? __ldcs(bufB + base + 32 + lane) : make_uint2(0u, 0u);
+    for (int j0 = 0; j0 < nl; j0 += 4) {             // four sub-lists per round, two loads each
+      int n4[4];
+      const uint2* buf4[4];
+      int nmax = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n_u = (int)__shfl_sync(ptx::FULL_MASK, my_n, min(j0 + u, 31));
+        n4[u] = j0 + u < nl ? n_u : 0;
+        buf4[u] = p.rowbuf + ((size_t)qi * p.nlists + l0 + min(j0 + u, nl - 1)) * p.CAP;
+        nmax = max(nmax, n4[u]);
+      }
+      for (int base = 0; base < nmax; base += 64) {
+        uint2 e[8];
+        bool ok[8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const bool pass = ok[u] && __uint_as_float(e[u].x) >= tau;
+          ok[2 * u] = base + lane < n4[u];
+          ok[2 * u + 1] = base + 32 + lane < n4[u];
+          e[2 * u] = ok[2 * u] ? __ldcs(buf4[u] + base + lane) : make_uint2(0u, 0u);
+          e[2 * u + 1] = ok[2 * u + 1] ? __ldcs(buf4[u] + base + 32 + lane) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ev = __uint_as_float(e[u].x);
+          const bool pass = ok[u] && (cut_strict ? ev > cut : ev >= cut);
           const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
           if (pass) wb[fill + __popc(mask & ((1u << lane) - 1u))] = e[u];
           fill += __popc(mask);
         }
-        if (fill > RESCORE_WBUF - 128) {
+        if (fill >= 32) {
           __syncwarp();
-          rescore_drain(wb, fill, cv, cidx, lane);
-          fill = 0;
+          while (fill >= 32) {                       // newest first: the tail of the buffer
+            rescore_merge32(wb, fill - 32, fill, cv, cidx, lane);
+            fill -= 32;
+          }
+          const float worst = __shfl_sync(ptx::FULL_MASK, cv, 31);
+          if (worst > cut || (worst == cut && worst > -INFINITY)) {
+            cut = worst;
+            cut_strict = true;                       // ties with the 32nd best cannot displace it
+          }
           __syncwarp();
         }
       }
     }
   }
   __syncwarp();
-  if (certified) rescore_drain(wb, fill, cv, cidx, lane);
+  if (certified && fill > 0) rescore_merge32(wb, 0, fill, cv, cidx, lane);
   const bool valid = (int)cidx >= 0;
   const int n_valid = __popc(__ballot_sync(ptx::FULL_MASK, valid));
   if (n_valid < min(32, p.G)) certified = false;          // candidates are missing
@@ -279,16 +296,17 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
         const int idx = __shfl_sync(ptx::FULL_MASK, (int)cidx, min(c0 + u, ns - 1));
         gs[u] = load_slice(p.g + (size_t)idx * 256, lane);
       }
+      float part[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float p0, p1;
-        sqdiff_dot2(qs, gs[u], w0, w1, p0, p1);
-        const float l0 = ptx::warp_sum(p0) + b0;
-        const float l1 = ptx::warp_sum(p1) + b1;
-        if (lane == c0 + u) {
-          my_l0 = l0;
-          my_l1 = l1;
-        }
+      for (int u = 0; u < 4; ++u) sqdiff_dot2(qs, gs[u], w0, w1, part[2 * u], part[2 * u + 1]);
+      const float tot = ptx::treduce<8>(part, lane);   // lane l: total of part[l % 8]
+      // candidate c0+u keeps its own pair: l0 from lane 2u, l1 from lane 2u+1
+      const int u_mine = lane - c0;
+      const float l0 = __shfl_sync(ptx::FULL_MASK, tot, (2 * u_mine) & 7) + b0;
+      const float l1 = __shfl_sync(ptx::FULL_MASK, tot, (2 * u_mine + 1) & 7) + b1;
+      if (u_mine >= 0 && u_mine < 4) {
+        my_l0 = l0;
+        my_l1 = l1;
       }
     }
   }

@@ -195,10 +195,40 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
   return v;
 }
+// same total as warp_sum but associated like treduce<8> (lane distances 4, 2, 1, 8, 16), so that a
+// value summed either way is bit-identical
+__device__ __forceinline__ float warp_sum_b(float v) {
+  v += __shfl_xor_sync(FULL_MASK, v, 4);
+  v += __shfl_xor_sync(FULL_MASK, v, 2);
+  v += __shfl_xor_sync(FULL_MASK, v, 1);
+  v += __shfl_xor_sync(FULL_MASK, v, 8);
+  v += __shfl_xor_sync(FULL_MASK, v, 16);
+  return v;
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
   return v;
+}
+
+// Transposing butterfly: N per-lane values (N = 8, 16, 32) are summed over the 32 lanes; lane l
+// returns the total of v[l % N].
+template <int N>
+__device__ __forceinline__ float treduce(float (&v)[N], int lane) {
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL_MASK, send, half);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int o = N; o < 32; o <<= 1) r += __shfl_xor_sync(FULL_MASK, r, o);
+  return r;
 }
 
 }  // namespace ptx
