@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
                                                            float* __restrict__ rq, float* __restrict__ anorm,
                                                            uint32_t* __restrict__ thr_global,
                                                            uint32_t* __restrict__ rowcnt, int nlists,
+                                                           float* __restrict__ gmax,
                                                            uint32_t* __restrict__ rowflag,
                                                            int32_t* __restrict__ counters) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   n2 = ptx::warp_sum(n2);
   amax = ptx::warp_max(amax);
   for (int l = lane; l < nlists; l += 32) rowcnt[(size_t)i * nlists + l] = 0;
+  for (int l = lane; l < nlists * 8; l += 32) gmax[(size_t)i * nlists * 8 + l] = -INFINITY;
   if (lane == 0) {
     rq[i] = r;
     anorm[i] = sqrtf(n2);
@@ -150,6 +152,7 @@ struct RescoreParams {
   const uint32_t* rowcnt;      // (Q,nlists)
   const uint32_t* rowflag;     // (Q)
   const uint32_t* thr_global;  // (Q)
+  const float* gmax;           // (Q,nlists,8) final group maxima (disjoint column groups)
   const float* rq;
   const float* anorm;
   const float* gstat;
@@ -216,6 +219,27 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   // they are swept four at a time with eight loads per lane in flight.
   float cut = tau;                                 // max(tau, 32nd best so far); entries equal to tau pass
   bool cut_strict = false;
+  {
+    // A tighter start: the row's group maxima belong to pairwise distinct gallery items, so the
+    // 32nd largest of them (here: its ordered-integer image truncated to 14 bits, found MSB
+    // first) also bounds the 32nd best -- with ~40 instead of ~300 items above it.
+    const int nval = p.nlists * 8;
+    const float* gmp = p.gmax + (size_t)qi * nval;
+    uint32_t key[3];
+    int nk = 0;
+    for (int i = lane; i < nval && nk < 3; i += 32) key[nk++] = ptx::float_to_ordered(gmp[i]);
+    if (nval <= 96) {
+      uint32_t K = 0;
+      for (int b = 31; b >= 18; --b) {
+        const uint32_t T = K | (1u << b);
+        int c = 0;
+        for (int j = 0; j < nk; ++j) c += key[j] >= T;
+        if (__reduce_add_sync(ptx::FULL_MASK, c) >= 32) K = T;
+      }
+      const float tt = ptx::ordered_to_float(K);
+      if (K != 0 && tt > cut) cut = tt;              // K == 0: fewer than 32 finite maxima
+    }
+  }
   for (int l0 = 0; l0 < p.nlists && certified; l0 += 32) {
     const int my_l = l0 + lane;
     uint32_t my_n = my_l < p.nlists ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;

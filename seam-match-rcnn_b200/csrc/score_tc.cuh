@@ -17,7 +17,7 @@
 // Bounds are shared between the 4 threads of a row through shared memory after every tile and
 // between CTAs working on the same rows through global memory (atomicMax on an
 // order-preserving integer image of the float).  To warm the bound before anything is
-// appended, every segment first sweeps a few sample tiles spread over the gallery in
+// appended, every segment first sweeps a few sample tiles spread over its range in
 // threshold-only mode.
 //
 // Work decomposition: the (query tile, gallery tile) grid is linearised query-major and cut
@@ -74,6 +74,7 @@ struct Params {
   uint32_t* rowcnt;           // (Q, P, 4) entries in each sub-list
   uint32_t* rowflag;          // (Q) nonzero: the row lost candidates, must be ranked exhaustively
   uint2* rowbuf;              // (Q, P, 4, CAP) {v, shard-local gallery row}
+  float* gmax;                // (Q, P, 4, 8) final group maxima of each thread's own (non-sample) columns
 };
 
 // contiguous tile range of CTA b out of nb
@@ -86,12 +87,15 @@ __device__ __forceinline__ int cta_of_tile(long long total, int nb, long long t)
   return (int)(((t + 1) * nb + total - 1) / total) - 1;
 }
 
-// One segment = query tile m, gallery tiles [nt0, nt0 + n_main), preceded by n_seed sample tiles.
+// One segment = query tile m, gallery tiles [nt0, nt0 + n_main), preceded by n_seed sample tiles
+// (threshold-only previews of tiles spread over the same range).
 struct Segment {
   int m, nt0, n_main, n_seed, ntiles_n;
   __device__ __forceinline__ int count() const { return n_seed + n_main; }
   __device__ __forceinline__ int tile(int i) const {
-    return i < n_seed ? (int)(((long long)(2 * i + 1) * ntiles_n) / (2 * n_seed)) : nt0 + (i - n_seed);
+    // sample tiles are taken from the segment's own range, so that every group maximum a thread
+    // ever records belongs to a column of its own piece (pieces of a row are disjoint)
+    return i < n_seed ? nt0 + (int)(((long long)(2 * i + 1) * n_main) / (2 * n_seed)) : nt0 + (i - n_seed);
   }
 };
 __device__ __forceinline__ Segment segment_at(const Params& p, long long t, long long t_end, long long& next) {
@@ -414,7 +418,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       // ---- segment end: publish the list length, the bound and the loss flag
       if (row_ok) {
-        if (slot_ok) p.rowcnt[li] = (uint32_t)((wp - wp_begin) >> 3);
+        if (slot_ok) {
+          p.rowcnt[li] = (uint32_t)((wp - wp_begin) >> 3);
+          float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
+          gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
+          gd[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+        }
         if (lossy) atomicOr(p.rowflag + grow, 1u);
         atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
       }

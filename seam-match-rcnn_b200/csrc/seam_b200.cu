@@ -427,7 +427,7 @@ int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float
 struct ScorePlan {
   int num_mtiles, ntiles_n, grid, P, CAP, nseed;
   long long total_tiles;
-  size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_rowflag, off_rowbuf, off_cnt, off_rows, total;
+  size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_gmax, off_rowflag, off_rowbuf, off_cnt, off_rows, total;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -482,6 +482,7 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
   s.off_anorm = o;   o += align_up((size_t)Q * 4, 256);
   s.off_thr = o;     o += align_up((size_t)Q * 4, 256);
   s.off_rowcnt = o;  o += align_up((size_t)Q * nlists * 4, 256);
+  s.off_gmax = o;    o += align_up((size_t)Q * nlists * 8 * 4, 256);
   s.off_rowflag = o; o += align_up((size_t)Q * 4, 256);
   s.off_rowbuf = o;  o += align_up((size_t)Q * nlists * s.CAP * 8 + (size_t)s.CAP * 8, 256);   // + slack to align the base
   s.off_cnt = o;     o += 256;
@@ -557,6 +558,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   float* anorm = reinterpret_cast<float*>(ws + s.off_anorm);
   uint32_t* thr = reinterpret_cast<uint32_t*>(ws + s.off_thr);
   uint32_t* rowcnt = reinterpret_cast<uint32_t*>(ws + s.off_rowcnt);
+  float* gmax = reinterpret_cast<float*>(ws + s.off_gmax);
   uint32_t* rowflag = reinterpret_cast<uint32_t*>(ws + s.off_rowflag);
   // sub-lists are aligned to their (power-of-two) size so that none straddles a 4 GiB boundary
   uint2* rowbuf = reinterpret_cast<uint2*>(
@@ -567,7 +569,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   {
     ProfileScope prof(h, SEAM_KERNEL_PREP_QUERIES, stream);
     exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt,
-                                                               s.P * score::NQ, rowflag, counters);
+                                                               s.P * score::NQ, gmax, rowflag, counters);
     SEAM_LAUNCHED(h, "prep_queries_kernel");
   }
 
@@ -590,6 +592,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.rowcnt = rowcnt;
   sp.rowflag = rowflag;
   sp.rowbuf = rowbuf;
+  sp.gmax = gmax;
   {
     ProfileScope prof(h, SEAM_KERNEL_SCORE, stream);
     score::score_topk_kernel<<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
@@ -604,6 +607,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   rp.rowcnt = rowcnt;
   rp.rowflag = rowflag;
   rp.thr_global = thr;
+  rp.gmax = gmax;
   rp.rq = rq;
   rp.anorm = anorm;
   rp.gstat = gstat;
