@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   n2 = ptx::warp_sum(n2);
   amax = ptx::warp_max(amax);
   for (int l = lane; l < nlists; l += 32) rowcnt[(size_t)i * nlists + l] = 0;
-  for (int l = lane; l < nlists * 8; l += 32) gmax[(size_t)i * nlists * 8 + l] = -INFINITY;
+  for (int l = lane; l < nlists * 16; l += 32) gmax[(size_t)i * nlists * 16 + l] = -INFINITY;
   if (lane == 0) {
     rq[i] = r;
     anorm[i] = sqrtf(n2);
@@ -152,7 +152,7 @@ struct RescoreParams {
   const uint32_t* rowcnt;      // (Q,nlists)
   const uint32_t* rowflag;     // (Q)
   const uint32_t* thr_global;  // (Q)
-  const float* gmax;           // (Q,nlists,8) final group maxima (disjoint column groups)
+  const float* gmax;           // (Q,nlists,16) final group maxima (disjoint column groups)
   const float* rq;
   const float* anorm;
   const float* gstat;
@@ -223,17 +223,23 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     // A tighter start: the row's group maxima belong to pairwise distinct gallery items, so the
     // 32nd largest of them (here: its ordered-integer image truncated to 14 bits, found MSB
     // first) also bounds the 32nd best -- with ~40 instead of ~300 items above it.
-    const int nval = p.nlists * 8;
+    const int nval = p.nlists * 16;
     const float* gmp = p.gmax + (size_t)qi * nval;
-    uint32_t key[3];
+    uint32_t key[8];
     int nk = 0;
-    for (int i = lane; i < nval && nk < 3; i += 32) key[nk++] = ptx::float_to_ordered(gmp[i]);
-    if (nval <= 96) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = lane + 32 * u;
+      key[u] = i < nval ? ptx::float_to_ordered(gmp[i]) : 0u;
+    }
+    nk = 8;
+    if (nval <= 256) {
       uint32_t K = 0;
       for (int b = 31; b >= 18; --b) {
         const uint32_t T = K | (1u << b);
         int c = 0;
-        for (int j = 0; j < nk; ++j) c += key[j] >= T;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c += key[j] >= T;
         if (__reduce_add_sync(ptx::FULL_MASK, c) >= 32) K = T;
       }
       const float tt = ptx::ordered_to_float(K);

@@ -8,12 +8,13 @@
 // fp32 accumulation in TMEM), + cg_j in the epilogue.  The (Q,G) matrix never leaves the SM.
 //
 // Candidate filter (branch-free).  Every query row keeps a lower bound thr on its 32nd best v:
-// the row's columns are dealt into 32 disjoint groups (4 epilogue threads per row x 8 running
-// group maxima each, one FMNMX3 per two accumulator elements); the smallest of the 32 group
-// maxima has at least 32 distinct gallery items at or above it, hence is such a bound.  An
-// element is appended to the row's candidate list in global memory iff v > thr (one predicated
-// 8-byte store).  Nothing is ever pruned or re-ordered on the SM; the re-score kernel
-// (score_exact.cuh) selects the best 32 of a row's list and certifies the result.
+// each of the row's 4 epilogue threads deals its columns into 16 disjoint groups and keeps their
+// running maxima (one FMNMX3 per two accumulator elements); at least 8 distinct gallery items
+// sit at or above the 8th largest of a thread's 16 maxima, so the smallest of the four threads'
+// values is such a bound -- with about 60 items above it (a plain minimum over 32 groups would
+// leave 125).  An element is appended to the row's candidate list in global memory iff v > thr
+// (one predicated 8-byte store).  Nothing is ever pruned or re-ordered on the SM; the re-score
+// kernel (score_exact.cuh) selects the best 32 of a row's list and certifies the result.
 // Bounds are shared between the 4 threads of a row through shared memory after every tile and
 // between CTAs working on the same rows through global memory (atomicMax on an
 // order-preserving integer image of the float).  To warm the bound before anything is
@@ -47,7 +48,8 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int NQ = 4;                  // column quarters = sub-lists per (row, piece)
 constexpr int QCOLS = BN / NQ;         // 64 accumulator columns per thread per tile
 constexpr int HALF = 32;               // columns per tcgen05.ld
-constexpr int GROUPS = 8;              // running group maxima per thread (4 threads x 8 = 32 per row)
+constexpr int GROUPS = 16;             // running group maxima per thread; its bound is their 8th largest
+                                       // (4 threads x 8 guaranteed items = 32 per row)
 constexpr uint32_t A_KB_BYTES = BM * BK * 2;
 constexpr uint32_t B_ST_BYTES = BN * BK * 2;
 
@@ -74,7 +76,8 @@ struct Params {
   uint32_t* rowcnt;           // (Q, P, 4) entries in each sub-list
   uint32_t* rowflag;          // (Q) nonzero: the row lost candidates, must be ranked exhaustively
   uint2* rowbuf;              // (Q, P, 4, CAP) {v, shard-local gallery row}
-  float* gmax;                // (Q, P, 4, 8) final group maxima of each thread's own (non-sample) columns
+  float* gmax;                // (Q, P, 4, 16) final group maxima of each thread (disjoint column groups)
+  unsigned long long* cta_ns; // (grid, 2) optional: {duration in ns, segments} per CTA (developer diagnostics)
 };
 
 // contiguous tile range of CTA b out of nb
@@ -98,13 +101,18 @@ struct Segment {
     return i < n_seed ? nt0 + (int)(((long long)(2 * i + 1) * n_main) / (2 * n_seed)) : nt0 + (i - n_seed);
   }
 };
-__device__ __forceinline__ Segment segment_at(const Params& p, long long t, long long t_end, long long& next) {
+// A segment that begins within the CTA's first WARM_TILES tiles previews min(nseed, n_main) sample
+// tiles: the whole grid starts cold at the same moment.  Later segments start from the bound the
+// other CTAs sweeping the same rows have published in thr_global (every 8 tiles) instead.
+constexpr int WARM_TILES = 16;
+__device__ __forceinline__ Segment segment_at(const Params& p, long long t_begin, long long t, long long t_end,
+                                              long long& next) {
   Segment s;
   s.m = (int)(t / p.ntiles_n);
   s.nt0 = (int)(t - (long long)s.m * p.ntiles_n);
   next = min(t_end, (long long)(s.m + 1) * p.ntiles_n);
   s.n_main = (int)(next - t);
-  s.n_seed = (p.nseed > 0 && s.n_main >= 4 * p.nseed) ? p.nseed : 0;
+  s.n_seed = (t - t_begin < WARM_TILES) ? min(p.nseed, s.n_main) : 0;
   s.ntiles_n = p.ntiles_n;
   return s;
 }
@@ -117,6 +125,42 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 __device__ __forceinline__ float min3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// ---- the 8th largest of 16 values -------------------------------------------------------
+#define SEAM_CE_DESC(a, b)          \
+  {                                 \
+    const float hi_ = fmaxf(a, b);  \
+    const float lo_ = fminf(a, b);  \
+    a = hi_;                        \
+    b = lo_;                        \
+  }
+// 19-comparator sorting network, descending
+__device__ __forceinline__ void sort8_desc(float (&s)[8]) {
+  SEAM_CE_DESC(s[0], s[1]) SEAM_CE_DESC(s[2], s[3]) SEAM_CE_DESC(s[4], s[5]) SEAM_CE_DESC(s[6], s[7])
+  SEAM_CE_DESC(s[0], s[2]) SEAM_CE_DESC(s[1], s[3]) SEAM_CE_DESC(s[4], s[6]) SEAM_CE_DESC(s[5], s[7])
+  SEAM_CE_DESC(s[1], s[2]) SEAM_CE_DESC(s[5], s[6]) SEAM_CE_DESC(s[0], s[4]) SEAM_CE_DESC(s[3], s[7])
+  SEAM_CE_DESC(s[1], s[5]) SEAM_CE_DESC(s[2], s[6])
+  SEAM_CE_DESC(s[1], s[4]) SEAM_CE_DESC(s[3], s[6])
+  SEAM_CE_DESC(s[2], s[4]) SEAM_CE_DESC(s[3], s[5])
+  SEAM_CE_DESC(s[3], s[4])
+}
+// At least 8 of the 16 values are >= the result (each is the maximum of a distinct column group,
+// so 8 distinct gallery items are).  With the halves sorted descending, the k-th largest of the
+// union is max over i+j=k of min(a_i, b_j) (1-based, a_0 = b_0 = +inf).
+__device__ __forceinline__ float eighth_largest_of_16(const float (&gm)[16]) {
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = gm[i];
+    b[i] = gm[8 + i];
+  }
+  sort8_desc(a);
+  sort8_desc(b);
+  float r = fmaxf(a[7], b[7]);
+#pragma unroll
+  for (int i = 1; i <= 7; ++i) r = fmaxf(r, fminf(a[i - 1], b[7 - i]));
   return r;
 }
 
@@ -159,7 +203,7 @@ __device__ __forceinline__ void tmem_ld_wait_x32(uint32_t (&a)[32]) {
 
 // 16 accumulator columns of one row (r[OFF..OFF+16)): + cg, append what beats cmp, fold into
 // the 8 group maxima (two columns per group and call)
-template <int OFF, int... E>
+template <int OFF, int GOFF, int... E>
 __device__ __forceinline__ void filter16_impl(const uint32_t (&r)[32], const float* cgp, float (&gm)[GROUPS],
                                               uint64_t& wp, float cmp, uint32_t col0,
                                               std::integer_sequence<int, E...>) {
@@ -175,13 +219,13 @@ __device__ __forceinline__ void filter16_impl(const uint32_t (&r)[32], const flo
   float v[16];
   ((v[E] = add_append<OFF + E>(wp, r[OFF + E], cgv[E], cmp, col0)), ...);
 #pragma unroll
-  for (int g = 0; g < GROUPS; ++g) gm[g] = max3(gm[g], v[g], v[g + 8]);
+  for (int g = 0; g < 8; ++g) gm[GOFF + g] = max3(gm[GOFF + g], v[g], v[g + 8]);
 }
 // 32 accumulator columns of one row
 __device__ __forceinline__ void filter32(const uint32_t (&r)[32], const float* cgp, float (&gm)[GROUPS], uint64_t& wp,
                                          float cmp, uint32_t col0) {
-  filter16_impl<0>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
-  filter16_impl<16>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
+  filter16_impl<0, 0>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
+  filter16_impl<16, 8>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -236,6 +280,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   long long t_begin, t_end;
   cta_range(p.total_tiles, gridDim.x, blockIdx.x, t_begin, t_end);
+  const uint64_t dbg_t0 = p.cta_ns ? ptx::globaltimer_ns() : 0;
 
   if (warp == 0) {
     // ================================================================= TMA producer
@@ -243,7 +288,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t stage = 0, sphase = 0, iphase = 0;
       long long t = t_begin, next;
       while (t < t_end) {
-        const Segment sg = segment_at(p, t, t_end, next);
+        const Segment sg = segment_at(p, t_begin, t, t_end, next);
         ptx::mbar_wait(a_empty, iphase ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, NKB * A_KB_BYTES);
         for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, sg.m * BM);
@@ -272,7 +317,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t stage = 0, sphase = 0, iphase = 0, acc = 0, aphase = 0;
       long long t = t_begin, next;
       while (t < t_end) {
-        const Segment sg = segment_at(p, t, t_end, next);
+        const Segment sg = segment_at(p, t_begin, t, t_end, next);
         const int n = sg.count();
         ptx::mbar_wait(a_full, iphase);
         for (int i = 0; i < n; ++i) {
@@ -310,7 +355,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc = 0, aphase = 0;
     long long t = t_begin, next;
     while (t < t_end) {
-      const Segment sg = segment_at(p, t, t_end, next);
+      const Segment sg = segment_at(p, t_begin, t, t_end, next);
       const int n = sg.count();
       for (int i = 0; i < n; ++i) {
         const int j0 = sg.tile(i) * BN + lane * 8;
@@ -339,7 +384,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc = 0, aphase = 0;
     long long t = t_begin, next;
     while (t < t_end) {
-      const Segment sg = segment_at(p, t, t_end, next);
+      const Segment sg = segment_at(p, t_begin, t, t_end, next);
       const int n = sg.count();
       const int grow = sg.m * BM + R;
       const bool row_ok = grow < p.Q;
@@ -398,13 +443,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         filter32(r, cgp + HALF, gm, wp, cmp, col0 + HALF);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&cg_empty[acc]);
-        // share the bound: 32 disjoint groups per row = 4 threads x 8 maxima
-        {
-          const float m0 = min3(gm[0], gm[1], gm[2]);
-          const float m1 = min3(gm[3], gm[4], gm[5]);
-          const float mine = min3(m0, m1, fminf(gm[6], gm[7]));
-          thr_x[R * NQ + cq] = mine;
-          const float4 o = *reinterpret_cast<const float4*>(thr_x + R * NQ);   // partners' values may be stale: still valid
+        // share the bound: each of the row's 4 threads vouches for 8 distinct items at or above the
+        // 8th largest of its 16 group maxima (re-derived every other tile), the smallest of the four
+        // values therefore for 32
+        const bool seed_end = (i + 1 == sg.n_seed);
+        if ((i & 1) || seed_end) {
+          thr_x[R * NQ + cq] = eighth_largest_of_16(gm);
+          // After the sample sweep the four warps of a row meet once, so that the first appended
+          // tile already sees all four bounds; later reads may be stale (still valid bounds).
+          if (seed_end) ptx::named_bar_sync(2 + lq, 4 * 32);
+          const float4 o = *reinterpret_cast<const float4*>(thr_x + R * NQ);
           thr = fmaxf(thr, fminf(fminf(o.x, o.y), fminf(o.z, o.w)));
         }
         if ((i & 7) == 7 && row_ok) {        // exchange with the other CTAs sweeping these rows
@@ -423,6 +471,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
           gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
           gd[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+          gd[2] = make_float4(gm[8], gm[9], gm[10], gm[11]);
+          gd[3] = make_float4(gm[12], gm[13], gm[14], gm[15]);
         }
         if (lossy) atomicOr(p.rowflag + grow, 1u);
         atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
@@ -433,6 +483,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cta_ns && tid == 0) {
+    p.cta_ns[2 * blockIdx.x] = ptx::globaltimer_ns() - dbg_t0;
+    p.cta_ns[2 * blockIdx.x + 1] = (unsigned long long)(t_end / p.ntiles_n - t_begin / p.ntiles_n + 1);
+  }
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 

@@ -447,6 +447,10 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
   if (s.ntiles_n < 1) s.ntiles_n = 1;
   s.total_tiles = (long long)s.num_mtiles * s.ntiles_n;
   s.grid = s.total_tiles < num_sms ? (int)s.total_tiles : num_sms;
+  {
+    const int cap_grid = env_int("SEAM_DEBUG_SCORE_GRID", 0);   // developer diagnostics only
+    if (cap_grid > 0 && cap_grid < s.grid) s.grid = cap_grid;
+  }
   const long long min_range = s.total_tiles / s.grid;           // shortest per-CTA range (>= 1)
   const long long max_range = (s.total_tiles + s.grid - 1) / s.grid;
   long long segs = (s.ntiles_n + min_range - 1) / min_range + 1;
@@ -482,7 +486,7 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
   s.off_anorm = o;   o += align_up((size_t)Q * 4, 256);
   s.off_thr = o;     o += align_up((size_t)Q * 4, 256);
   s.off_rowcnt = o;  o += align_up((size_t)Q * nlists * 4, 256);
-  s.off_gmax = o;    o += align_up((size_t)Q * nlists * 8 * 4, 256);
+  s.off_gmax = o;    o += align_up((size_t)Q * nlists * score::GROUPS * 4, 256);
   s.off_rowflag = o; o += align_up((size_t)Q * 4, 256);
   s.off_rowbuf = o;  o += align_up((size_t)Q * nlists * s.CAP * 8 + (size_t)s.CAP * 8, 256);   // + slack to align the base
   s.off_cnt = o;     o += 256;
@@ -593,6 +597,10 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.rowflag = rowflag;
   sp.rowbuf = rowbuf;
   sp.gmax = gmax;
+  // developer diagnostics: SEAM_DEBUG_CTA_NS=1 records per-CTA durations at the tail of the fallback-row list
+  sp.cta_ns = (env_int("SEAM_DEBUG_CTA_NS", 0) && (size_t)Q * 4 >= 8192)
+                  ? reinterpret_cast<unsigned long long*>(ws + s.off_rows + (((size_t)Q * 4 - 4096) & ~(size_t)7))
+                  : nullptr;
   {
     ProfileScope prof(h, SEAM_KERNEL_SCORE, stream);
     score::score_topk_kernel<<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
