@@ -19,6 +19,7 @@
 // tf32-exact halves r_hi + r_lo for the tensor-core product M r of K1b (nlb_tc.cuh).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include "fold.cuh"
 #include "sm100_ptx.cuh"
 
@@ -160,129 +161,139 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
     const int len = slot_len[slot];
     const float* xs = xbuf + (size_t)slot * TR * D;
 
-    // ---- frames -> registers, four dots per frame
-    float4 x0[TR], x1[TR];
-    constexpr int N1 = NV <= 16 ? 16 : 32;                       // first butterfly: frames 0..7
-    constexpr int N2 = NV <= 32 ? 1 : (NV - 32 <= 8 ? 8 : 32);    // second butterfly: frames 8..
-    float acc[N1], acc2[N2];
-#pragma unroll
-    for (int i = 0; i < N1; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < N2; ++i) acc2[i] = 0.f;
-#pragma unroll
-    for (int t = 0; t < TR; ++t) {
-      if (t < len) {
-        x0[t] = *reinterpret_cast<const float4*>(xs + t * D + 4 * lane);
-        x1[t] = *reinterpret_cast<const float4*>(xs + t * D + 128 + 4 * lane);
-      } else {
-        x0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        x1[t] = x0[t];
-      }
-      const float va = dot4(x0[t], ut0) + dot4(x1[t], ut1);
-      const float vd = dot4(x0[t], wa0) + dot4(x1[t], wa1);
-      const float vb = dot4(x0[t], up0) + dot4(x1[t], up1);
-      const float vc = dot4(x0[t], ug0) + dot4(x1[t], ug1);
-      if (4 * t < 32) {
-        acc[4 * t + 0] = va;
-        acc[4 * t + 1] = vd;
-        acc[4 * t + 2] = vb;
-        acc[4 * t + 3] = vc;
-      } else {
-        acc2[4 * t - 32 + 0] = va;
-        acc2[4 * t - 32 + 1] = vd;
-        acc2[4 * t - 32 + 2] = vb;
-        acc2[4 * t - 32 + 3] = vc;
-      }
-    }
-    if constexpr (NV <= 16) {
-      const float tot = treduce<16>(acc, lane);
-      if (lane < 16) scal[lane] = tot + my_const;
-    } else {
-      const float tot = treduce<32>(acc, lane);
-      scal[lane] = tot + my_const;
-      if constexpr (NV > 32) {
-        if constexpr (N2 == 8) {
-          const float tot2 = treduce<8>(acc2, lane);
-          if (lane < 8) scal[32 + lane] = tot2 + my_const;
+    // One body, two instantiations: tracks with all TR frames (the common case) run without
+    // per-frame guards and with unrolled T x T loops.
+    auto process = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      // ---- frames -> registers, four dots per frame
+      float4 x0[TR], x1[TR];
+      constexpr int N1 = NV <= 16 ? 16 : 32;                       // first butterfly: frames 0..7
+      constexpr int N2 = NV <= 32 ? 1 : (NV - 32 <= 8 ? 8 : 32);    // second butterfly: frames 8..
+      float acc[N1], acc2[N2];
+  #pragma unroll
+      for (int i = 0; i < N1; ++i) acc[i] = 0.f;
+  #pragma unroll
+      for (int i = 0; i < N2; ++i) acc2[i] = 0.f;
+  #pragma unroll
+      for (int t = 0; t < TR; ++t) {
+        if (FULL || t < len) {
+          x0[t] = *reinterpret_cast<const float4*>(xs + t * D + 4 * lane);
+          x1[t] = *reinterpret_cast<const float4*>(xs + t * D + 128 + 4 * lane);
         } else {
-          const float tot2 = treduce<32>(acc2, lane);
-          scal[32 + lane] = tot2 + my_const;
+          x0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+          x1[t] = x0[t];
+        }
+        const float va = dot4(x0[t], ut0) + dot4(x1[t], ut1);
+        const float vd = dot4(x0[t], wa0) + dot4(x1[t], wa1);
+        const float vb = dot4(x0[t], up0) + dot4(x1[t], up1);
+        const float vc = dot4(x0[t], ug0) + dot4(x1[t], ug1);
+        if (4 * t < 32) {
+          acc[4 * t + 0] = va;
+          acc[4 * t + 1] = vd;
+          acc[4 * t + 2] = vb;
+          acc[4 * t + 3] = vc;
+        } else {
+          acc2[4 * t - 32 + 0] = va;
+          acc2[4 * t - 32 + 1] = vd;
+          acc2[4 * t - 32 + 2] = vb;
+          acc2[4 * t - 32 + 3] = vc;
         }
       }
-    }
-    __syncwarp();
+      if constexpr (NV <= 16) {
+        const float tot = treduce<16>(acc, lane);
+        if (lane < 16) scal[lane] = tot + my_const;
+      } else {
+        const float tot = treduce<32>(acc, lane);
+        scal[lane] = tot + my_const;
+        if constexpr (NV > 32) {
+          if constexpr (N2 == 8) {
+            const float tot2 = treduce<8>(acc2, lane);
+            if (lane < 8) scal[32 + lane] = tot2 + my_const;
+          } else {
+            const float tot2 = treduce<32>(acc2, lane);
+            scal[32 + lane] = tot2 + my_const;
+          }
+        }
+      }
+      __syncwarp();
 
-    // ---- attention over the track's frames (lane = frame)
-    const bool valid = lane < len;
-    const float inv_len = len > 0 ? 1.f / (float)len : 0.f;
-    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) sc = *reinterpret_cast<const float4*>(scal + 4 * lane);   // a, d, b, c of my frame
-    float sum = 0.f;
-    if (len > 1) {
-      for (int j = 0; j < len; ++j) {
-        const float2 bc = *reinterpret_cast<const float2*>(scal + 4 * j + 2);
-        sum = fmaf(fmaxf(sc.x + bc.x, 0.f) * inv_len, bc.y, sum);
+      // ---- attention over the track's frames (lane = frame)
+      const int L = FULL ? TR : len;                   // compile-time trip counts for full tracks
+      const bool valid = lane < L;
+      const float inv_len = FULL ? 1.f / (float)TR : (len > 0 ? 1.f / (float)len : 0.f);
+      float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) sc = *reinterpret_cast<const float4*>(scal + 4 * lane);   // a, d, b, c of my frame
+      float sum = 0.f;
+      if (FULL ? TR > 1 : len > 1) {
+  #pragma unroll
+        for (int j = 0; j < (FULL ? TR : len); ++j) {
+          const float2 bc = *reinterpret_cast<const float2*>(scal + 4 * j + 2);
+          sum = fmaf(fmaxf(sc.x + bc.x, 0.f) * inv_len, bc.y, sum);
+        }
       }
-    }
-    const float s_t = valid ? sc.y + sum + c_s : -INFINITY;
-    const float m = ptx::warp_max(s_t);
-    const float e_t = valid ? expf(s_t - m) : 0.f;
-    const float z = ptx::warp_sum(e_t);
-    const float p_t = valid ? e_t / z : 0.f;
-    __syncwarp();                                    // all lanes have read b, c, d
-    if (lane < TR) {
-      scal[4 * lane + 1] = p_t;
-      scal[4 * lane + 2] = p_t;
-    }
-    __syncwarp();
-    float q_j = 0.f;
-    if (len > 1 && valid) {
-      for (int t = 0; t < len; ++t) {
-        const float2 ap = *reinterpret_cast<const float2*>(scal + 4 * t);
-        q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
+      const float s_t = valid ? sc.y + sum + c_s : -INFINITY;
+      const float m = ptx::warp_max(s_t);
+      const float e_t = valid ? expf(s_t - m) : 0.f;
+      const float z = ptx::warp_sum(e_t);
+      const float p_t = valid ? e_t / z : 0.f;
+      __syncwarp();                                    // all lanes have read b, c, d
+      if (lane < TR) {
+        scal[4 * lane + 1] = p_t;
+        scal[4 * lane + 2] = p_t;
       }
-    }
-    if (lane < TR) scal[4 * lane + 3] = q_j;
-    const float qsum = ptx::warp_sum(q_j);
-    if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
-    __syncwarp();
+      __syncwarp();
+      float q_j = 0.f;
+      if ((FULL ? TR > 1 : len > 1) && valid) {
+  #pragma unroll
+        for (int t = 0; t < (FULL ? TR : len); ++t) {
+          const float2 ap = *reinterpret_cast<const float2*>(scal + 4 * t);
+          q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
+        }
+      }
+      if (lane < TR) scal[4 * lane + 3] = q_j;
+      const float qsum = ptx::warp_sum(q_j);
+      if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
+      __syncwarp();
 
-    // ---- weighted sums over frames, 8 channels per lane
-    float4 po0 = make_float4(0.f, 0.f, 0.f, 0.f), po1 = po0, r0 = po0, r1 = po0;
-#pragma unroll
-    for (int t = 0; t < TR; ++t) {
-      if (t < len) {
-        const float2 pq = *reinterpret_cast<const float2*>(scal + 4 * t + 2);
-        fma4(po0, pq.x, x0[t]);
-        fma4(po1, pq.x, x1[t]);
-        fma4(r0, pq.y, x0[t]);
-        fma4(r1, pq.y, x1[t]);
+      // ---- weighted sums over frames, 8 channels per lane
+      float4 po0 = make_float4(0.f, 0.f, 0.f, 0.f), po1 = po0, r0 = po0, r1 = po0;
+  #pragma unroll
+      for (int t = 0; t < TR; ++t) {
+        if (FULL || t < len) {
+          const float2 pq = *reinterpret_cast<const float2*>(scal + 4 * t + 2);
+          fma4(po0, pq.x, x0[t]);
+          fma4(po1, pq.x, x1[t]);
+          fma4(r0, pq.y, x0[t]);
+          fma4(r1, pq.y, x1[t]);
+        }
       }
-    }
-    if (len > 1) {
-      const float4 wbg0 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 4 * lane);
-      const float4 wbg1 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 128 + 4 * lane);
-      const float4 bw0 = *reinterpret_cast<const float4*>(fold + Fold::BW + 4 * lane);
-      const float4 bw1 = *reinterpret_cast<const float4*>(fold + Fold::BW + 128 + 4 * lane);
-      po0.x += fmaf(qsum, wbg0.x, bw0.x);
-      po0.y += fmaf(qsum, wbg0.y, bw0.y);
-      po0.z += fmaf(qsum, wbg0.z, bw0.z);
-      po0.w += fmaf(qsum, wbg0.w, bw0.w);
-      po1.x += fmaf(qsum, wbg1.x, bw1.x);
-      po1.y += fmaf(qsum, wbg1.y, bw1.y);
-      po1.z += fmaf(qsum, wbg1.z, bw1.z);
-      po1.w += fmaf(qsum, wbg1.w, bw1.w);
-    }
-    float4 h0, l0, h1, l1;
-    split_tf32(r0, h0, l0);
-    split_tf32(r1, h1, l1);
-    const size_t o = (size_t)track * D + 4 * lane;
-    *reinterpret_cast<float4*>(p.pooled + o) = po0;
-    *reinterpret_cast<float4*>(p.pooled + o + 128) = po1;
-    *reinterpret_cast<float4*>(p.r_hi + o) = h0;
-    *reinterpret_cast<float4*>(p.r_hi + o + 128) = h1;
-    *reinterpret_cast<float4*>(p.r_lo + o) = l0;
-    *reinterpret_cast<float4*>(p.r_lo + o + 128) = l1;
+      if (FULL ? TR > 1 : len > 1) {
+        const float4 wbg0 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 4 * lane);
+        const float4 wbg1 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 128 + 4 * lane);
+        const float4 bw0 = *reinterpret_cast<const float4*>(fold + Fold::BW + 4 * lane);
+        const float4 bw1 = *reinterpret_cast<const float4*>(fold + Fold::BW + 128 + 4 * lane);
+        po0.x += fmaf(qsum, wbg0.x, bw0.x);
+        po0.y += fmaf(qsum, wbg0.y, bw0.y);
+        po0.z += fmaf(qsum, wbg0.z, bw0.z);
+        po0.w += fmaf(qsum, wbg0.w, bw0.w);
+        po1.x += fmaf(qsum, wbg1.x, bw1.x);
+        po1.y += fmaf(qsum, wbg1.y, bw1.y);
+        po1.z += fmaf(qsum, wbg1.z, bw1.z);
+        po1.w += fmaf(qsum, wbg1.w, bw1.w);
+      }
+      float4 h0, l0, h1, l1;
+      split_tf32(r0, h0, l0);
+      split_tf32(r1, h1, l1);
+      const size_t o = (size_t)track * D + 4 * lane;
+      *reinterpret_cast<float4*>(p.pooled + o) = po0;
+      *reinterpret_cast<float4*>(p.pooled + o + 128) = po1;
+      *reinterpret_cast<float4*>(p.r_hi + o) = h0;
+      *reinterpret_cast<float4*>(p.r_hi + o + 128) = h1;
+      *reinterpret_cast<float4*>(p.r_lo + o) = l0;
+      *reinterpret_cast<float4*>(p.r_lo + o + 128) = l1;
+    };
+    if (len == TR) process(std::true_type{});
+    else process(std::false_type{});
   }
 }
 

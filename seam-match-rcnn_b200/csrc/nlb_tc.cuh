@@ -111,26 +111,44 @@ nlb_tc_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ 
       ptx::umma_commit(d_full);
     }
   } else if (warp >= 4) {
+    // Epilogue.  A thread owns one track row of the accumulator, but a row-per-thread walk over
+    // global memory would touch 32 different 1 KB rows per instruction; each warp therefore
+    // transposes 32x32 blocks through a padded tile in the (now idle) operand stages, so that
+    // every global access is one 128-byte line.
     const int ew = warp - 4;
-    const int row = row0 + ew * 32 + lane;
     ptx::mbar_wait(d_full, 0);
     ptx::tc_fence_after();
+    float* tile = reinterpret_cast<float*>(smem) + ew * (32 * 33);
     const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16);
+    const int rbase = row0 + ew * 32;
+    // pooled' for chunk ch+1 is fetched (32 independent 128-byte lines per warp) while chunk ch is
+    // transposed and written
+    float pl[32], pn[32];
+    auto fetch = [&](int ch, float (&dst)[32]) {
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const int row = rbase + rr;
+        dst[rr] = row < p.rows ? __ldg(p.pooled + (size_t)row * 256 + ch * 32 + lane) : 0.f;
+      }
+    };
+    fetch(0, pl);
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
+      if (ch + 1 < BN / 32) fetch(ch + 1, pn);
       uint32_t r[32];
       ptx::tmem_ld_x32(taddr + ch * 32, r);
       ptx::tmem_ld_wait();
-      if (row < p.rows) {
-        const float4* src = reinterpret_cast<const float4*>(p.pooled + (size_t)row * 256 + ch * 32);
-        float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * 256 + ch * 32);
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 pl = src[c4];
-          dst[c4] = make_float4(pl.x + __uint_as_float(r[c4 * 4 + 0]), pl.y + __uint_as_float(r[c4 * 4 + 1]),
-                                pl.z + __uint_as_float(r[c4 * 4 + 2]), pl.w + __uint_as_float(r[c4 * 4 + 3]));
-        }
+      for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = __uint_as_float(r[c]);
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const int row = rbase + rr;
+        if (row < p.rows) p.out[(size_t)row * 256 + ch * 32 + lane] = pl[rr] + tile[rr * 33 + lane];
       }
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) pl[rr] = pn[rr];
     }
   }
 
