@@ -46,9 +46,9 @@ struct Cfg;
 template <>
 struct Cfg<4> { static constexpr int NW = 16, SLOTS = 3; };
 template <>
-struct Cfg<10> { static constexpr int NW = 10, SLOTS = 2; };
+struct Cfg<10> { static constexpr int NW = 12, SLOTS = 1; };
 template <>
-struct Cfg<16> { static constexpr int NW = 7, SLOTS = 2; };
+struct Cfg<16> { static constexpr int NW = 8, SLOTS = 1; };
 
 template <int TR>
 constexpr size_t smem_bytes() {
@@ -147,16 +147,20 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
   const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
                        : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
 
+  // SLOTS == 1: the single buffer is re-armed for the next track as soon as the current one's
+  // frames sit in registers, so its copy overlaps the rest of the computation.
 #pragma unroll 1
-  for (int i = 0; i < SLOTS - 1; ++i) issue(first + i * stride, i);
+  for (int i = 0; i < (SLOTS == 1 ? 1 : SLOTS - 1); ++i) issue(first + i * stride, i);
 
   int it = 0;
 #pragma unroll 1
   for (long long track = first; track < p.Q; track += stride, ++it) {
     const int slot = it % SLOTS;
     const uint32_t phase = (uint32_t)(it / SLOTS) & 1u;
-    __syncwarp();                                    // every lane is done with the slot being refilled
-    issue(track + (long long)(SLOTS - 1) * stride, (it + SLOTS - 1) % SLOTS);
+    if constexpr (SLOTS > 1) {
+      __syncwarp();                                  // every lane is done with the slot being refilled
+      issue(track + (long long)(SLOTS - 1) * stride, (it + SLOTS - 1) % SLOTS);
+    }
     ptx::mbar_wait(&bars[slot], phase);
     const int len = slot_len[slot];
     const float* xs = xbuf + (size_t)slot * TR * D;
@@ -198,6 +202,10 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
           acc2[4 * t - 32 + 2] = vb;
           acc2[4 * t - 32 + 3] = vc;
         }
+      }
+      if constexpr (SLOTS == 1) {
+        __syncwarp();                                // all lanes hold their frames in registers
+        issue(track + stride, 0);
       }
       if constexpr (NV <= 16) {
         const float tot = treduce<16>(acc, lane);
