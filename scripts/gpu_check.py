@@ -25,7 +25,8 @@ def engine():
 
 
 def stage_agg(e):
-    for (Q, T, rag) in [(64, 10, None), (37, 4, (0, 4)), (5, 1, None), (8, 64, None), (301, 10, (1, 10)), (1000, 3, None)]:
+    for (Q, T, rag) in [(64, 10, None), (37, 4, (0, 4)), (5, 1, None), (8, 64, None), (301, 10, (1, 10)), (1000, 3, None),
+                        (77, 40, (0, 40)), (33, 64, (1, 64)), (40, 17, None), (21, 33, (30, 33))]:
         seq, mask, lens = so.synth_tracks(Q, T, seed=Q + T, ragged=rag)
         ref, att = so.aggregate_tracks(seq, mask, W)
         out, a = e.aggregate(seq.to(dev), mask.to(dev), getatt=True)

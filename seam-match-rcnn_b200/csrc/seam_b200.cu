@@ -14,8 +14,8 @@
 #include <cuda_runtime.h>
 
 #include "../../include/seam_b200.h"
-#include "aggregate.cuh"
 #include "aggregate_warp.cuh"
+#include "aggregate_group.cuh"
 #include "fold.cuh"
 #include "nlb_gemm.cuh"
 #include "nlb_tc.cuh"
@@ -170,7 +170,6 @@ int seam_create(seam_handle** out, int device) {
   }
   h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   // opt in to large dynamic shared memory once
-  cudaFuncSetAttribute(agg::aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(agg::Smem));
   cudaFuncSetAttribute(score::score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -179,6 +178,10 @@ int seam_create(seam_handle** out, int device) {
                        (int)aggw::smem_bytes<10>());
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)aggw::smem_bytes<16>());
+  cudaFuncSetAttribute(aggg::aggregate_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(aggg::Smem<2>));
+  cudaFuncSetAttribute(aggg::aggregate_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(aggg::Smem<4>));
   cudaFuncSetAttribute(nlbtc::nlb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nlbtc::SMEM_BYTES);
   cudaFuncSetAttribute(nlbgemm::nlb_full_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)((SEAM_MAX_T * 257 + 2 * SEAM_MAX_T) * sizeof(float)));
@@ -298,47 +301,32 @@ int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const 
 
   {
     ProfileScope prof(h, SEAM_KERNEL_AGGREGATE, stream);
-    if (Tmax <= 16) {
-      aggw::Params p;
-      p.seq = seq;
-      p.mask = mask;
-      p.lens = lens;
-      p.Tmax = Tmax;
-      p.Q = Q;
-      p.frame_stride = frame_stride;
-      p.track_stride = track_stride;
-      p.fold = h->fold;
-      p.pooled = pooled;
-      p.r_hi = r_hi;
-      p.r_lo = r_lo;
-      p.att = att;
-      if (Tmax <= 4) launch_aggregate_warp<4>(p, h->num_sms, stream);
-      else if (Tmax <= 10) launch_aggregate_warp<10>(p, h->num_sms, stream);
-      else launch_aggregate_warp<16>(p, h->num_sms, stream);
-      SEAM_LAUNCHED(h, "aggregate_warp_kernel");
-    } else {
-      agg::Params p;
-      p.seq = seq;
-      p.mask = mask;
-      p.lens = lens;
-      p.Tmax = Tmax;
-      p.Q = Q;
-      p.NT = agg::ROWS_MAX / Tmax;
-      if (p.NT > agg::MAX_NT) p.NT = agg::MAX_NT;
-      if (p.NT < 1) p.NT = 1;
-      p.rows = p.NT * Tmax;
-      p.num_tiles = (Q + p.NT - 1) / p.NT;
-      p.frame_stride = frame_stride;
-      p.track_stride = track_stride;
-      p.fold = h->fold;
-      p.pooled = pooled;
-      p.r_hi = r_hi;
-      p.r_lo = r_lo;
-      p.att = att;
-      const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
-      agg::aggregate_kernel<<<grid, agg::THREADS, sizeof(agg::Smem), stream>>>(p);
-      SEAM_LAUNCHED(h, "aggregate_kernel");
+    aggw::Params p;
+    p.seq = seq;
+    p.mask = mask;
+    p.lens = lens;
+    p.Tmax = Tmax;
+    p.Q = Q;
+    p.frame_stride = frame_stride;
+    p.track_stride = track_stride;
+    p.fold = h->fold;
+    p.pooled = pooled;
+    p.r_hi = r_hi;
+    p.r_lo = r_lo;
+    p.att = att;
+    if (Tmax <= 4) launch_aggregate_warp<4>(p, h->num_sms, stream);
+    else if (Tmax <= 10) launch_aggregate_warp<10>(p, h->num_sms, stream);
+    else if (Tmax <= 16) launch_aggregate_warp<16>(p, h->num_sms, stream);
+    else if (Tmax <= 32) {   // two warps per track
+      const int want = (Q + 3) / 4;
+      aggg::aggregate_group_kernel<2><<<want < h->num_sms ? want : h->num_sms, aggg::THREADS, sizeof(aggg::Smem<2>),
+                                        stream>>>(p);
+    } else {                 // 33..64 frames: four warps per track
+      const int want = (Q + 1) / 2;
+      aggg::aggregate_group_kernel<4><<<want < h->num_sms ? want : h->num_sms, aggg::THREADS, sizeof(aggg::Smem<4>),
+                                        stream>>>(p);
     }
+    SEAM_LAUNCHED(h, "aggregate kernel");
   }
 
   // K1b: out = pooled' + (r_hi + r_lo) M^T on the tensor cores

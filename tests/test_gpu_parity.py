@@ -53,6 +53,27 @@ def test_aggregate_strided_input(weights, engine):
     assert (out.cpu() - ref).abs().max() <= TOL_EMB
 
 
+@pytest.mark.parametrize("Q,T,ragged", [(40, 17, None), (21, 32, (1, 32)), (77, 40, (0, 40)), (33, 64, (1, 64)),
+                                        (12, 16, (0, 16)), (50, 11, (1, 11))])
+def test_aggregate_every_kernel_variant(Q, T, ragged, weights, engine):
+    """One case per aggregation kernel: warp-per-track (T <= 4 / 10 / 16 are covered by the golden cases
+    and here by T = 11..16), two warps per track (17..32 frames), four warps per track (33..64),
+    ragged lengths including empty and single-frame tracks; mask path and lens path."""
+    seq, mask, lens = so.synth_tracks(Q, T, seed=Q + T, ragged=ragged)
+    ref, att = so.aggregate_tracks(seq, mask, weights)
+    out, a = engine.aggregate(seq.to(DEV), mask.to(DEV), getatt=True)
+    assert (out.cpu() - ref).abs().max() <= TOL_EMB
+    aref = torch.zeros(Q, T)
+    for i, p in enumerate(att):
+        aref[i, :p.shape[0]] = p[:, 0]
+    assert (a.cpu() - aref).abs().max() <= TOL_ATT
+    out2 = engine.aggregate(seq.to(DEV), None, lens=torch.as_tensor(lens))
+    assert torch.equal(out2, out)
+    single = torch.as_tensor(lens) == 1                      # the reference skips the block for T == 1
+    if single.any():
+        assert torch.equal(out.cpu()[single], seq[1][single])
+
+
 def test_aggregate_empty_and_limits(engine):
     assert engine.aggregate(torch.zeros(1, 5, 256, device=DEV)).abs().sum() == 0     # Tmax == 0
     assert engine.aggregate(torch.zeros(4, 0, 256, device=DEV)).shape == (0, 256)    # Q == 0
