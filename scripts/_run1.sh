@@ -1,4 +1,5 @@
-timeout 500 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/gpu_check.py agg topk misc > gpurun_out/r10_memcheck.log 2>&1; echo memcheck rc=$?
-grep -E "ERROR SUMMARY|Invalid|error" gpurun_out/r10_memcheck.log | head -10
-timeout 400 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/gpu_check.py agg > gpurun_out/r10_racecheck.log 2>&1; echo racecheck rc=$?
-grep -E "RACECHECK SUMMARY|hazard|Race" gpurun_out/r10_racecheck.log | head -10
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+python scripts/gpu_time.py 15000 10 15000 2>&1 | tail -1
+python scripts/gpu_time.py 10000 10 125000 2>&1 | tail -1
+SEAM_DEBUG_SCORE_MODE=1 python scripts/gpu_time.py 15000 10 15000 2>&1 | tail -1 | cut -c1-160
+python scripts/_dbg_cta.py 2>&1 | tail -5 | head -3

@@ -25,9 +25,9 @@
 // into one contiguous, equally long range per CTA; a range is processed as at most a few
 // "segments" (one query tile x a run of gallery tiles).
 //
-// Roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
-// allocator, warp 3 = stages cg tiles, warps 4..19 = epilogue (warp%4 selects the TMEM lane
-// quarter = 32 query rows, (warp-4)/4 the 64-column quarter of the tile).
+// Roles (608 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
+// allocator, then stages cg tiles, warps 3..18 = epilogue (warp%4 selects the TMEM lane quarter =
+// 32 query rows, (warp-3)/4 the 64-column quarter of the tile).
 // Tile: 128 queries x 256 gallery rows, K = 256 as 4 k-blocks of 64 fp16 (128-byte swizzle).
 // The A (query) tile stays resident in shared memory for a whole segment; B (gallery)
 // k-blocks stream through a 4-stage ring; two 256-column TMEM accumulators alternate, and an
@@ -42,12 +42,13 @@ namespace seam {
 namespace score {
 
 constexpr int BM = 128, BN = 256, BK = 64, NKB = 4, NSTAGE = 4;
-constexpr int CTRL_WARPS = 4, EPI_WARPS = 16;
+constexpr int CTRL_WARPS = 3, EPI_WARPS = 16;   // 608 threads, 96 registers each (warps are allocated in fours)
 constexpr int THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int NQ = 4;                  // column quarters = sub-lists per (row, piece)
 constexpr int QCOLS = BN / NQ;         // 64 accumulator columns per thread per tile
 constexpr int HALF = 32;               // columns per tcgen05.ld
+constexpr int CMD_SEED = 1, CMD_SEG_START = 2, CMD_SEG_END = 4, CMD_SEED_END = 8;
 constexpr int GROUPS = 16;             // running group maxima per thread; its bound is their 8th largest
                                        // (4 threads x 8 guaranteed items = 32 per row)
 constexpr uint32_t A_KB_BYTES = BM * BK * 2;
@@ -57,7 +58,8 @@ constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_B = OFF_A + NKB * A_KB_BYTES;
 constexpr uint32_t OFF_CG = OFF_B + NSTAGE * B_ST_BYTES;
 constexpr uint32_t OFF_THRX = OFF_CG + 2 * BN * 4;
-constexpr uint32_t OFF_BAR = OFF_THRX + BM * NQ * 4;
+constexpr uint32_t OFF_CMD = OFF_THRX + BM * NQ * 4;   // 2 x int4 tile commands
+constexpr uint32_t OFF_BAR = OFF_CMD + 2 * 16;
 constexpr uint32_t NUM_BARS = 2 * NSTAGE + 2 + 8;
 constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;   // + slack for manual 1024-byte alignment
@@ -98,7 +100,7 @@ struct Segment {
   __device__ __forceinline__ int tile(int i) const {
     // sample tiles are taken from the segment's own range, so that every group maximum a thread
     // ever records belongs to a column of its own piece (pieces of a row are disjoint)
-    return i < n_seed ? nt0 + (int)(((long long)(2 * i + 1) * n_main) / (2 * n_seed)) : nt0 + (i - n_seed);
+    return i < n_seed ? nt0 + (int)((unsigned)((2 * i + 1) * n_main) / (unsigned)(2 * n_seed)) : nt0 + (i - n_seed);
   }
 };
 // A segment that begins within the CTA's first WARM_TILES tiles previews min(nseed, n_main) sample
@@ -238,6 +240,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sB = smem + OFF_B;
   float* cg_s = reinterpret_cast<float*>(smem + OFF_CG);        // [2][BN]
   float* thr_x = reinterpret_cast<float*>(smem + OFF_THRX);     // [BM][NQ] group-minimum of each thread
+  int* cmd_s = reinterpret_cast<int*>(smem + OFF_CMD);           // [2][4] tile command of each accumulator slot
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
   uint64_t* empty = bars + NSTAGE;          // [NSTAGE]  MMA -> TMA
@@ -350,15 +353,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         t = next;
       }
     }
-  } else if (warp == 3) {
-    // ================================================================= cg stager
+  } else if (warp == 2) {
+    // ================================================================= tile director (after the TMEM allocation)
+    // Walks the CTA's tile sequence and, per tile, stages the cg values and a 16-byte command
+    // {gallery tile | -1 = done, flags, query tile, piece} for the epilogue warps, which therefore
+    // carry no segment bookkeeping of their own.
     uint32_t acc = 0, aphase = 0;
     long long t = t_begin, next;
     while (t < t_end) {
       const Segment sg = segment_at(p, t_begin, t, t_end, next);
       const int n = sg.count();
+      const int piece = blockIdx.x - cta_of_tile(p.total_tiles, gridDim.x, (long long)sg.m * p.ntiles_n);
       for (int i = 0; i < n; ++i) {
-        const int j0 = sg.tile(i) * BN + lane * 8;
+        const int nt = sg.tile(i);
+        const int j0 = nt * BN + lane * 8;
         float c[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) c[e] = (j0 + e < p.G) ? __ldg(p.cg + j0 + e) : -INFINITY;   // padded columns never qualify
@@ -366,6 +374,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float* dst = cg_s + acc * BN + lane * 8;
         *reinterpret_cast<float4*>(dst) = make_float4(c[0], c[1], c[2], c[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(c[4], c[5], c[6], c[7]);
+        if (lane == 0) {
+          const int flags = (i < sg.n_seed ? CMD_SEED : 0) | (i == 0 ? CMD_SEG_START : 0) |
+                            (i == n - 1 ? CMD_SEG_END : 0) | (i + 1 == sg.n_seed ? CMD_SEED_END : 0);
+          *reinterpret_cast<int4*>(cmd_s + acc * 4) = make_int4(nt, flags, sg.m, piece);
+        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&cg_full[acc]);
         if (++acc == 2) {
@@ -375,63 +388,69 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       t = next;
     }
+    ptx::mbar_wait(&cg_empty[acc], aphase ^ 1);
+    if (lane == 0) {
+      *reinterpret_cast<int4*>(cmd_s + acc * 4) = make_int4(-1, 0, 0, 0);
+      ptx::mbar_arrive(&cg_full[acc]);
+    }
   } else if (warp >= CTRL_WARPS) {
     // ================================================================= epilogue
     const int ew = warp - CTRL_WARPS;
-    const int lq = ew & 3;                   // TMEM lane quarter (must equal warp % 4)
+    const int lq = warp & 3;                 // TMEM lane quarter: hardware ties it to warp % 4
     const int cq = ew >> 2;                  // column quarter of the tile
     const int R = lq * 32 + lane;            // row within the CTA tile
     uint32_t acc = 0, aphase = 0;
-    long long t = t_begin, next;
-    while (t < t_end) {
-      const Segment sg = segment_at(p, t_begin, t, t_end, next);
-      const int n = sg.count();
-      const int grow = sg.m * BM + R;
-      const bool row_ok = grow < p.Q;
-      const int piece = blockIdx.x - cta_of_tile(p.total_tiles, gridDim.x, (long long)sg.m * p.ntiles_n);
-      const bool slot_ok = row_ok && piece >= 0 && piece < p.P;
-      const size_t li = slot_ok ? ((size_t)grow * p.P + piece) * NQ + cq : 0;
-      const uint64_t wp_begin = reinterpret_cast<uint64_t>(p.rowbuf + li * (size_t)p.CAP);
-      const uint64_t wp_limit = wp_begin + (uint64_t)(p.CAP - QCOLS) * 8;   // room for one more tile's 64 columns
-      uint64_t wp = wp_begin;
-      float thr = row_ok ? ptx::ordered_to_float(__ldcg(p.thr_global + grow)) : INFINITY;
-      bool closed = !slot_ok;                // the list takes no (more) entries
-      bool lossy = row_ok && !slot_ok;
-      float gm[GROUPS];
+    // per-segment state
+    int grow = 0, itile = 0;
+    bool row_ok = false, slot_ok = false, closed = true, lossy = false;
+    size_t li = 0;
+    uint64_t wp = 0;
+    uint32_t wlo_begin = 0, wlo_limit = 0;
+    float thr = INFINITY;
+    float gm[GROUPS];
+    for (;;) {
+      ptx::mbar_wait(&cg_full[acc], aphase);
+      const int4 cmd = *reinterpret_cast<const int4*>(cmd_s + acc * 4);
+      if (cmd.x < 0) break;
+      if (cmd.y & CMD_SEG_START) {
+        grow = cmd.z * BM + R;
+        row_ok = grow < p.Q;
+        slot_ok = row_ok && cmd.w >= 0 && cmd.w < p.P;
+        li = slot_ok ? ((size_t)grow * p.P + cmd.w) * NQ + cq : 0;   // this thread's sub-list
+        wp = reinterpret_cast<uint64_t>(p.rowbuf + li * (size_t)p.CAP);
+        // only the low address word ever changes (a sub-list never straddles a 4 GiB boundary)
+        wlo_begin = (uint32_t)wp;
+        wlo_limit = wlo_begin + (uint32_t)(p.CAP - QCOLS) * 8u;      // room for one more tile's 64 columns
+        thr = row_ok ? ptx::ordered_to_float(__ldcg(p.thr_global + grow)) : INFINITY;
+        closed = !slot_ok;                   // the list takes no (more) entries
+        lossy = row_ok && !slot_ok;
+        itile = 0;
 #pragma unroll
-      for (int g = 0; g < GROUPS; ++g) gm[g] = -INFINITY;
-      thr_x[R * NQ + cq] = -INFINITY;
-      ptx::named_bar_sync(1, EPI_THREADS);   // previous segment's bounds are gone before anyone reads
-
-      for (int i = 0; i < n; ++i) {
-        const int nt = sg.tile(i);
-        ptx::mbar_wait(&t_full[acc], aphase);
-        ptx::tc_fence_after();
-        if (p.mode == 1) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::mbar_wait(&cg_full[acc], aphase);
-            ptx::mbar_arrive(&t_empty[acc]);
-            ptx::mbar_arrive(&cg_empty[acc]);
-          }
-          if (++acc == 2) {
-            acc = 0;
-            aphase ^= 1;
-          }
-          continue;
+        for (int g = 0; g < GROUPS; ++g) gm[g] = -INFINITY;
+        thr_x[R * NQ + cq] = -INFINITY;
+        ptx::named_bar_sync(1, EPI_THREADS); // previous segment's bounds are gone before anyone reads
+      }
+      ptx::mbar_wait(&t_full[acc], aphase);
+      ptx::tc_fence_after();
+      if (p.mode == 1) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&t_empty[acc]);
+          ptx::mbar_arrive(&cg_empty[acc]);
         }
+      } else {
+        const bool seed = (cmd.y & CMD_SEED) != 0;
         const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + acc * BN + cq * QCOLS;
-        if (i >= sg.n_seed && wp > wp_limit && !closed) {   // no room for another tile: stop appending,
-          closed = true;                                    // the row goes to the exhaustive path
+        if (!seed && (uint32_t)wp > wlo_limit && !closed) {   // no room for another tile: stop appending,
+          closed = true;                                      // the row goes to the exhaustive path
           lossy = true;
         }
-        const float cmp = (closed || i < sg.n_seed) ? INFINITY : thr;
+        const float cmp = (closed || seed) ? INFINITY : thr;
         const float* cgp = cg_s + acc * BN + cq * QCOLS;
-        const uint32_t col0 = (uint32_t)(nt * BN + cq * QCOLS);
+        const uint32_t col0 = (uint32_t)(cmd.x * BN + cq * QCOLS);
         uint32_t r[32];
         ptx::tmem_ld_x32(taddr, r);
-        ptx::mbar_wait(&cg_full[acc], aphase);
         tmem_ld_wait_x32(r);
         filter32(r, cgp, gm, wp, cmp, col0);
         ptx::tmem_ld_x32(taddr + HALF, r);
@@ -446,8 +465,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // share the bound: each of the row's 4 threads vouches for 8 distinct items at or above the
         // 8th largest of its 16 group maxima (re-derived every other tile), the smallest of the four
         // values therefore for 32
-        const bool seed_end = (i + 1 == sg.n_seed);
-        if ((i & 1) || seed_end) {
+        const bool seed_end = (cmd.y & CMD_SEED_END) != 0;
+        if ((itile & 1) || seed_end) {
           thr_x[R * NQ + cq] = eighth_largest_of_16(gm);
           // After the sample sweep the four warps of a row meet once, so that the first appended
           // tile already sees all four bounds; later reads may be stale (still valid bounds).
@@ -455,29 +474,29 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float4 o = *reinterpret_cast<const float4*>(thr_x + R * NQ);
           thr = fmaxf(thr, fminf(fminf(o.x, o.y), fminf(o.z, o.w)));
         }
-        if ((i & 7) == 7 && row_ok) {        // exchange with the other CTAs sweeping these rows
+        if ((itile & 7) == 7 && row_ok) {    // exchange with the other CTAs sweeping these rows
           const uint32_t old = atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
           thr = fmaxf(thr, ptx::ordered_to_float(old));
         }
-        if (++acc == 2) {
-          acc = 0;
-          aphase ^= 1;
+        ++itile;
+        // ---- segment end: publish the list length, the bound and the loss flag
+        if ((cmd.y & CMD_SEG_END) && row_ok) {
+          if (slot_ok) {
+            p.rowcnt[li] = ((uint32_t)wp - wlo_begin) >> 3;
+            float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
+            gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
+            gd[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+            gd[2] = make_float4(gm[8], gm[9], gm[10], gm[11]);
+            gd[3] = make_float4(gm[12], gm[13], gm[14], gm[15]);
+          }
+          if (lossy) atomicOr(p.rowflag + grow, 1u);
+          atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
         }
       }
-      // ---- segment end: publish the list length, the bound and the loss flag
-      if (row_ok) {
-        if (slot_ok) {
-          p.rowcnt[li] = (uint32_t)((wp - wp_begin) >> 3);
-          float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
-          gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
-          gd[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
-          gd[2] = make_float4(gm[8], gm[9], gm[10], gm[11]);
-          gd[3] = make_float4(gm[12], gm[13], gm[14], gm[15]);
-        }
-        if (lossy) atomicOr(p.rowflag + grow, 1u);
-        atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
+      if (++acc == 2) {
+        acc = 0;
+        aphase ^= 1;
       }
-      t = next;
     }
   }
 
