@@ -203,31 +203,30 @@ __device__ __forceinline__ void tmem_ld_wait_x32(uint32_t (&a)[32]) {
                : "memory");
 }
 
-// 16 accumulator columns of one row (r[OFF..OFF+16)): + cg, append what beats cmp, fold into
-// the 8 group maxima (two columns per group and call)
-template <int OFF, int GOFF, int... E>
-__device__ __forceinline__ void filter16_impl(const uint32_t (&r)[32], const float* cgp, float (&gm)[GROUPS],
+// 16 accumulator columns of one row: + cg, append what beats cmp, fold into 8 of the 16 group
+// maxima (two columns per group and call; GOFF selects the half)
+template <int GOFF, int... E>
+__device__ __forceinline__ void filter16_impl(const uint32_t (&r)[16], const float* cgp, float (&gm)[GROUPS],
                                               uint64_t& wp, float cmp, uint32_t col0,
                                               std::integer_sequence<int, E...>) {
   float cgv[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
-    const float4 g4 = *reinterpret_cast<const float4*>(cgp + OFF + c4 * 4);
+    const float4 g4 = *reinterpret_cast<const float4*>(cgp + c4 * 4);
     cgv[c4 * 4 + 0] = g4.x;
     cgv[c4 * 4 + 1] = g4.y;
     cgv[c4 * 4 + 2] = g4.z;
     cgv[c4 * 4 + 3] = g4.w;
   }
   float v[16];
-  ((v[E] = add_append<OFF + E>(wp, r[OFF + E], cgv[E], cmp, col0)), ...);
+  ((v[E] = add_append<E>(wp, r[E], cgv[E], cmp, col0)), ...);
 #pragma unroll
   for (int g = 0; g < 8; ++g) gm[GOFF + g] = max3(gm[GOFF + g], v[g], v[g + 8]);
 }
-// 32 accumulator columns of one row
-__device__ __forceinline__ void filter32(const uint32_t (&r)[32], const float* cgp, float (&gm)[GROUPS], uint64_t& wp,
+template <int GOFF>
+__device__ __forceinline__ void filter16(const uint32_t (&r)[16], const float* cgp, float (&gm)[GROUPS], uint64_t& wp,
                                          float cmp, uint32_t col0) {
-  filter16_impl<0, 0>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
-  filter16_impl<16, 8>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
+  filter16_impl<GOFF>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -449,17 +448,24 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float cmp = (closed || seed) ? INFINITY : thr;
         const float* cgp = cg_s + acc * BN + cq * QCOLS;
         const uint32_t col0 = (uint32_t)(cmd.x * BN + cq * QCOLS);
-        uint32_t r[32];
-        ptx::tmem_ld_x32(taddr, r);
-        tmem_ld_wait_x32(r);
-        filter32(r, cgp, gm, wp, cmp, col0);
-        ptx::tmem_ld_x32(taddr + HALF, r);
-        tmem_ld_wait_x32(r);
+        // four chunks of 16 columns: the next chunk is in flight while the current one is filtered
+        uint32_t ra[16], rb[16];
+        ptx::tmem_ld_x16(taddr, ra);
+        ptx::tmem_ld_wait_x16(ra);
+        ptx::tmem_ld_x16(taddr + 16, rb);
+        filter16<0>(ra, cgp, gm, wp, cmp, col0);
+        ptx::tmem_ld_wait_x16(rb);
+        ptx::tmem_ld_x16(taddr + 32, ra);
+        filter16<8>(rb, cgp + 16, gm, wp, cmp, col0 + 16);
+        ptx::tmem_ld_wait_x16(ra);
+        ptx::tmem_ld_x16(taddr + 48, rb);
+        filter16<0>(ra, cgp + 32, gm, wp, cmp, col0 + 32);
+        ptx::tmem_ld_wait_x16(rb);
         // this warp's accumulator columns have all been read: hand the TMEM slot back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
-        filter32(r, cgp + HALF, gm, wp, cmp, col0 + HALF);
+        filter16<8>(rb, cgp + 48, gm, wp, cmp, col0 + 48);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&cg_empty[acc]);
         // share the bound: each of the row's 4 threads vouches for 8 distinct items at or above the
