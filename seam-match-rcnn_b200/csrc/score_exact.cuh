@@ -342,15 +342,17 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   }
   float d = in_S ? my_l1 - my_l0 : -INFINITY;
   int id = in_S ? (int)cidx : INT_MAX;
-  float sc = in_S ? softmax1(my_l0, my_l1) : 0.f;
   // observed error of the tensor-core value against the bound it was trusted with
   const float approx_d = cv + p.rq[qi] + p.fold[Fold::CONSTS + 4];
   const bool violated = in_S && !(fabsf(d - approx_d) <= eps + 2e-5f * (1.f + fabsf(d)));
   if (__any_sync(ptx::FULL_MASK, violated)) certified = false;
-  wsort::sort32_rank(d, id, sc, lane);
+  wsort::sort32_rank2(d, id, lane);
   if (lane < p.k) {
     const size_t o = (size_t)qi * p.k + lane;
     const bool ok = id != INT_MAX;
+    // softmax(l0, l1)[1] depends on the logits only through d = l1 - l0 (the larger logit is
+    // subtracted exactly), so it is formed after the sort: bit-identical to softmax1(l0, l1)
+    const float sc = softmax1(0.f, d);
     p.out_score[o] = ok ? sc : 0.f;
     p.out_margin[o] = d;
     p.out_idx[o] = ok ? id + p.index_offset : -1;

@@ -54,6 +54,25 @@ __device__ __forceinline__ void cmpx_rank(float& d, int& i, float& s, int lane, 
     s = os;
   }
 }
+// same order, no payload
+__device__ __forceinline__ void cmpx_rank2(float& d, int& i, int lane, int j, int k) {
+  const float od = __shfl_xor_sync(ptx::FULL_MASK, d, j);
+  const int oi = __shfl_xor_sync(ptx::FULL_MASK, i, j);
+  const bool up = (lane & k) == 0;
+  const bool lower = (lane & j) == 0;
+  const bool keep_better = (lower == up);
+  const bool take = keep_better ? ranks_before(od, oi, d, i) : ranks_before(d, i, od, oi);
+  if (take) {
+    d = od;
+    i = oi;
+  }
+}
+__device__ __forceinline__ void sort32_rank2(float& d, int& i, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) cmpx_rank2(d, i, lane, j, k);
+}
 // best first
 __device__ __forceinline__ void sort32_rank(float& d, int& i, float& s, int lane) {
 #pragma unroll
