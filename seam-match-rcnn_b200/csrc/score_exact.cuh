@@ -221,26 +221,35 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   bool cut_strict = false;
   {
     // A tighter start: the row's group maxima belong to pairwise distinct gallery items, so the
-    // 32nd largest of them (here: its ordered-integer image truncated to 14 bits, found MSB
+    // 32nd largest of them (here: its ordered-integer image to 10 significant bits, found MSB
     // first) also bounds the 32nd best -- with ~40 instead of ~300 items above it.
     const int nval = p.nlists * 16;
     const float* gmp = p.gmax + (size_t)qi * nval;
     uint32_t key[8];
-    int nk = 0;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int i = lane + 32 * u;
       key[u] = i < nval ? ptx::float_to_ordered(gmp[i]) : 0u;
     }
-    nk = 8;
     if (nval <= 256) {
-      uint32_t K = 0;
-      for (int b = 31; b >= 18; --b) {
-        const uint32_t T = K | (1u << b);
-        int c = 0;
+      // The answer lies between lo = the smallest lane maximum (32 distinct maxima are >= it) and
+      // hi = the largest maximum: only the bits below their common prefix need deciding.
+      uint32_t lmax = key[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c += key[j] >= T;
-        if (__reduce_add_sync(ptx::FULL_MASK, c) >= 32) K = T;
+      for (int j = 1; j < 8; ++j) lmax = max(lmax, key[j]);
+      const uint32_t hi = __reduce_max_sync(ptx::FULL_MASK, lmax);
+      const uint32_t lo = __reduce_min_sync(ptx::FULL_MASK, lmax);
+      uint32_t K = lo;
+      if (hi != lo) {
+        const int b0 = 31 - __clz(hi ^ lo);
+        K = hi & ~((2u << b0) - 1u);                  // common prefix; at least 32 keys are >= it
+        for (int b = b0; b >= 0 && b > b0 - 10; --b) {
+          const uint32_t T = K | (1u << b);
+          int c = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) c += key[j] >= T;
+          if (__reduce_add_sync(ptx::FULL_MASK, c) >= 32) K = T;
+        }
       }
       const float tt = ptx::ordered_to_float(K);
       if (K != 0 && tt > cut) cut = tt;              // K == 0: fewer than 32 finite maxima
