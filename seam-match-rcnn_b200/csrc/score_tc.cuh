@@ -399,12 +399,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int cq = ew >> 2;                  // column quarter of the tile
     const int R = lq * 32 + lane;            // row within the CTA tile
     uint32_t acc = 0, aphase = 0;
-    // per-segment state
+    // per-segment state, kept small: the tile prologue below is a serial chain that all four warps
+    // of a scheduler run at the same moment (they wake on the same barrier), so nothing hides it
+    constexpr uint32_t ST_ROW = 1, ST_SLOT = 2, ST_CLOSED = 4, ST_LOSSY = 8;
+    uint32_t st = ST_CLOSED;                 // flags | piece << 8
     int grow = 0, itile = 0;
-    bool row_ok = false, slot_ok = false, closed = true, lossy = false;
-    size_t li = 0;
     uint64_t wp = 0;
-    uint32_t wlo_begin = 0, wlo_limit = 0;
+    uint32_t wlo_begin = 0;
+    const uint32_t room = (uint32_t)(p.CAP - QCOLS) * 8u;   // a list closes when < one tile's 64 entries fit
     float thr = INFINITY;
     float gm[GROUPS];
     for (;;) {
@@ -413,16 +415,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (cmd.x < 0) break;
       if (cmd.y & CMD_SEG_START) {
         grow = cmd.z * BM + R;
-        row_ok = grow < p.Q;
-        slot_ok = row_ok && cmd.w >= 0 && cmd.w < p.P;
-        li = slot_ok ? ((size_t)grow * p.P + cmd.w) * NQ + cq : 0;   // this thread's sub-list
+        const bool row_ok = grow < p.Q;
+        const bool slot_ok = row_ok && cmd.w >= 0 && cmd.w < p.P;
+        const size_t li = slot_ok ? ((size_t)grow * p.P + cmd.w) * NQ + cq : 0;   // this thread's sub-list
         wp = reinterpret_cast<uint64_t>(p.rowbuf + li * (size_t)p.CAP);
-        // only the low address word ever changes (a sub-list never straddles a 4 GiB boundary)
-        wlo_begin = (uint32_t)wp;
-        wlo_limit = wlo_begin + (uint32_t)(p.CAP - QCOLS) * 8u;      // room for one more tile's 64 columns
+        wlo_begin = (uint32_t)wp;            // only the low address word ever changes (no 4 GiB straddle)
         thr = row_ok ? ptx::ordered_to_float(__ldcg(p.thr_global + grow)) : INFINITY;
-        closed = !slot_ok;                   // the list takes no (more) entries
-        lossy = row_ok && !slot_ok;
+        st = (row_ok ? ST_ROW : 0u) | (slot_ok ? ST_SLOT : ST_CLOSED) | ((row_ok && !slot_ok) ? ST_LOSSY : 0u) |
+             ((uint32_t)(cmd.w & 0xffff) << 8);
         itile = 0;
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) gm[g] = -INFINITY;
@@ -439,18 +439,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::mbar_arrive(&cg_empty[acc]);
         }
       } else {
-        const bool seed = (cmd.y & CMD_SEED) != 0;
+        // four chunks of 16 columns; the first load is issued before anything else is derived
         const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + acc * BN + cq * QCOLS;
-        if (!seed && (uint32_t)wp > wlo_limit && !closed) {   // no room for another tile: stop appending,
-          closed = true;                                      // the row goes to the exhaustive path
-          lossy = true;
-        }
-        const float cmp = (closed || seed) ? INFINITY : thr;
-        const float* cgp = cg_s + acc * BN + cq * QCOLS;
-        const uint32_t col0 = (uint32_t)(cmd.x * BN + cq * QCOLS);
-        // four chunks of 16 columns: the next chunk is in flight while the current one is filtered
         uint32_t ra[16], rb[16];
         ptx::tmem_ld_x16(taddr, ra);
+        const bool seed = (cmd.y & CMD_SEED) != 0;
+        if (!seed && !(st & ST_CLOSED) && (uint32_t)wp - wlo_begin > room)   // no room for another tile:
+          st |= ST_CLOSED | ST_LOSSY;                                         // the row goes to the exhaustive path
+        const float cmp = (seed || (st & ST_CLOSED)) ? INFINITY : thr;
+        const float* cgp = cg_s + acc * BN + cq * QCOLS;
+        const uint32_t col0 = (uint32_t)(cmd.x * BN + cq * QCOLS);
         ptx::tmem_ld_wait_x16(ra);
         ptx::tmem_ld_x16(taddr + 16, rb);
         filter16<0>(ra, cgp, gm, wp, cmp, col0);
@@ -480,14 +478,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float4 o = *reinterpret_cast<const float4*>(thr_x + R * NQ);
           thr = fmaxf(thr, fminf(fminf(o.x, o.y), fminf(o.z, o.w)));
         }
-        if ((itile & 7) == 7 && row_ok) {    // exchange with the other CTAs sweeping these rows
+        if ((itile & 7) == 7 && (st & ST_ROW)) {   // exchange with the other CTAs sweeping these rows
           const uint32_t old = atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
           thr = fmaxf(thr, ptx::ordered_to_float(old));
         }
         ++itile;
         // ---- segment end: publish the list length, the bound and the loss flag
-        if ((cmd.y & CMD_SEG_END) && row_ok) {
-          if (slot_ok) {
+        if ((cmd.y & CMD_SEG_END) && (st & ST_ROW)) {
+          if (st & ST_SLOT) {
+            const size_t li = ((size_t)grow * p.P + (st >> 8)) * NQ + cq;
             p.rowcnt[li] = ((uint32_t)wp - wlo_begin) >> 3;
             float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
             gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
@@ -495,7 +494,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             gd[2] = make_float4(gm[8], gm[9], gm[10], gm[11]);
             gd[3] = make_float4(gm[12], gm[13], gm[14], gm[15]);
           }
-          if (lossy) atomicOr(p.rowflag + grow, 1u);
+          if (st & ST_LOSSY) atomicOr(p.rowflag + grow, 1u);
           atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
         }
       }
