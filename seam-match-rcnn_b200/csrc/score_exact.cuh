@@ -20,6 +20,7 @@ constexpr float FP16_MAX = 65504.f;
 // bound on |fp16 tensor-core value - exact value| relative to ||a_i|| * max_j ||g_j||:
 // two operand roundings (2^-11 each) + fp32 accumulation slack.
 constexpr float EPS_COEFF = 9.9e-4f;   // 2^-10 = 9.77e-4, plus accumulation slack
+constexpr float TAG_REL_ERR = 8e-6f;   // > 2^-17 = 7.63e-6: 6 mantissa bits replaced by a column tag
 
 __device__ __forceinline__ float softmax1(float l0, float l1) {
   const float m = fmaxf(l0, l1);
@@ -148,8 +149,8 @@ struct RescoreParams {
   const float* q;        // (Q,256)
   const float* g;        // (G,256)
   const float* fold;
-  const uint2* rowbuf;         // (Q,nlists,CAP) {approximate value, shard-local gallery row}
-  const uint32_t* rowcnt;      // (Q,nlists)
+  const uint2* rowbuf;         // (Q,nlists,CAP x 8 bytes): CAP/2 quad records {w0,w1,w2,w3} per sub-list
+  const uint32_t* rowcnt;      // (Q,nlists) quad records in each sub-list
   const uint32_t* rowflag;     // (Q)
   const uint32_t* thr_global;  // (Q)
   const float* gmax;           // (Q,nlists,16) final group maxima (disjoint column groups)
@@ -174,7 +175,8 @@ struct RescoreParams {
 //  3. re-scores S in the fp32 direct form, orders it (margin desc, index asc), writes k entries.
 // Rows that cannot be certified (S fills the window, candidates were dropped, fp16 overflow,
 // or an observed |approximate - exact| above eps) go to the exhaustive kernel.
-constexpr int RESCORE_WBUF = 288;   // compaction buffer entries per warp (256 new + < 32 kept)
+constexpr int RS_SUBL = 4;          // sub-lists swept per round (one 16-byte load per lane each)
+constexpr int RESCORE_WBUF = 160;   // compaction buffer entries per warp (128 new + < 32 kept)
 
 // merge the entries wb[begin, begin+32) (fewer at the tail) into the running sorted best-32
 __device__ __forceinline__ void rescore_merge32(const uint2* wb, int begin, int end, float& cv, uint32_t& cidx,
@@ -202,6 +204,8 @@ __device__ __forceinline__ void rescore_merge32(const uint2* wb, int begin, int 
 
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   __shared__ uint2 wbuf[8][RESCORE_WBUF];
+  __shared__ uint4 qbuf[8][64];
+  __shared__ uint32_t qcol[8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * 8 + warp;
   if (qi >= p.Q) return;
@@ -255,66 +259,108 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
       if (K != 0 && tt > cut) cut = tt;              // K == 0: fewer than 32 finite maxima
     }
   }
+  // A record is a quad {w0,w1,w2,w3} of adjacent gallery rows (score_tc.cuh): the 6 low mantissa bits of
+  // w0 hold the quad's position inside its 64-column quarter, those of w1..w3 the gallery tile index;
+  // the quarter is the sub-list's index mod 4.  Two levels: quads whose maximum passes the cut are
+  // compacted into qb (one ballot per 32 quads); every 32 of those are expanded into elements, which
+  // are compacted into wb and merged into the best 32 as before.
+  const int capq = p.CAP / 2;
+  const uint4* rowq = reinterpret_cast<const uint4*>(p.rowbuf) + (size_t)qi * p.nlists * capq;
+  uint4* qb = qbuf[warp];
+  uint32_t* qc = qcol[warp];
+  int qfill = 0;
+  auto expand = [&](int start, int count) {
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t col = 0;
+    const bool have = lane < count;
+    if (have) {
+      rec = qb[start + lane];
+      col = qc[start + lane];
+    }
+    const uint32_t wv[4] = {rec.x, rec.y, rec.z, rec.w};
+#pragma unroll
+    for (int el = 0; el < 4; ++el) {
+      const float ev = __uint_as_float(wv[el]);
+      const bool pass = have && (cut_strict ? ev > cut : ev >= cut);
+      const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
+      if (mask == 0u) continue;                      // warp-uniform
+      if (pass) wb[fill + __popc(mask & ((1u << lane) - 1u))] = make_uint2(wv[el], col + el);
+      fill += __popc(mask);
+    }
+    if (fill >= 32) {                                // at most 128 new entries since the last check
+      __syncwarp();
+      while (fill >= 32) {                           // newest first: the tail of the buffer
+        rescore_merge32(wb, fill - 32, fill, cv, cidx, lane);
+        fill -= 32;
+      }
+      const float worst = __shfl_sync(ptx::FULL_MASK, cv, 31);
+      if (worst > cut || (worst == cut && worst > -INFINITY)) {
+        cut = worst;
+        cut_strict = true;                           // ties with the 32nd best cannot displace it
+      }
+    }
+    __syncwarp();
+  };
   for (int l0 = 0; l0 < p.nlists && certified; l0 += 32) {
     const int my_l = l0 + lane;
     uint32_t my_n = my_l < p.nlists ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
-    if (__any_sync(ptx::FULL_MASK, my_n > (uint32_t)p.CAP)) {
+    if (__any_sync(ptx::FULL_MASK, my_n > (uint32_t)capq)) {
       certified = false;
       break;
     }
     const int nl = min(32, p.nlists - l0);
-    for (int j0 = 0; j0 < nl; j0 += 4) {             // four sub-lists per round, two loads each
-      int n4[4];
-      const uint2* buf4[4];
+    for (int j0 = 0; j0 < nl; j0 += RS_SUBL) {       // RS_SUBL sub-lists per round, 32 quads of each
+      int n8[RS_SUBL];
+      const uint4* buf8[RS_SUBL];
       int nmax = 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < RS_SUBL; ++u) {
         const int n_u = (int)__shfl_sync(ptx::FULL_MASK, my_n, min(j0 + u, 31));
-        n4[u] = j0 + u < nl ? n_u : 0;
-        buf4[u] = p.rowbuf + ((size_t)qi * p.nlists + l0 + min(j0 + u, nl - 1)) * p.CAP;
-        nmax = max(nmax, n4[u]);
+        n8[u] = j0 + u < nl ? n_u : 0;
+        buf8[u] = rowq + (size_t)(l0 + min(j0 + u, nl - 1)) * capq;
+        nmax = max(nmax, n8[u]);
       }
-      for (int base = 0; base < nmax; base += 64) {
-        uint2 e[8];
-        bool ok[8];
+      for (int base = 0; base < nmax; base += 32) {
+        uint4 e[RS_SUBL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          ok[2 * u] = base + lane < n4[u];
-          ok[2 * u + 1] = base + 32 + lane < n4[u];
-          e[2 * u] = ok[2 * u] ? __ldcs(buf4[u] + base + lane) : make_uint2(0u, 0u);
-          e[2 * u + 1] = ok[2 * u + 1] ? __ldcs(buf4[u] + base + 32 + lane) : make_uint2(0u, 0u);
-        }
+        for (int u = 0; u < RS_SUBL; ++u)
+          e[u] = base + lane < n8[u] ? __ldcs(buf8[u] + base + lane) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float ev = __uint_as_float(e[u].x);
-          const bool pass = ok[u] && (cut_strict ? ev > cut : ev >= cut);
+        for (int u = 0; u < RS_SUBL; ++u) {
+          if (n8[u] <= base) continue;               // warp-uniform
+          const float m = fmaxf(fmaxf(__uint_as_float(e[u].x), __uint_as_float(e[u].y)),
+                                fmaxf(__uint_as_float(e[u].z), __uint_as_float(e[u].w)));
+          const bool pass = base + lane < n8[u] && (cut_strict ? m > cut : m >= cut);
           const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
-          if (pass) wb[fill + __popc(mask & ((1u << lane) - 1u))] = e[u];
-          fill += __popc(mask);
-        }
-        if (fill >= 32) {
-          __syncwarp();
-          while (fill >= 32) {                       // newest first: the tail of the buffer
-            rescore_merge32(wb, fill - 32, fill, cv, cidx, lane);
-            fill -= 32;
+          if (mask == 0u) continue;
+          if (pass) {
+            const uint32_t tile = (e[u].y & 63u) | ((e[u].z & 63u) << 6) | ((e[u].w & 63u) << 12);
+            const int pos = qfill + __popc(mask & ((1u << lane) - 1u));
+            qb[pos] = e[u];
+            qc[pos] = tile * 256u + (uint32_t)((l0 + j0 + u) & 3) * 64u + (e[u].x & 63u) * 4u;
           }
-          const float worst = __shfl_sync(ptx::FULL_MASK, cv, 31);
-          if (worst > cut || (worst == cut && worst > -INFINITY)) {
-            cut = worst;
-            cut_strict = true;                       // ties with the 32nd best cannot displace it
+          qfill += __popc(mask);
+          if (qfill >= 32) {
+            __syncwarp();
+            expand(qfill - 32, 32);
+            qfill -= 32;
           }
-          __syncwarp();
         }
       }
     }
   }
+  __syncwarp();
+  if (certified && qfill > 0) expand(0, qfill);
   __syncwarp();
   if (certified && fill > 0) rescore_merge32(wb, 0, fill, cv, cidx, lane);
   const bool valid = (int)cidx >= 0;
   const int n_valid = __popc(__ballot_sync(ptx::FULL_MASK, valid));
   if (n_valid < min(32, p.G)) certified = false;          // candidates are missing
   const float a_k = __shfl_sync(ptx::FULL_MASK, cv, min(p.k, 32) - 1);
-  const float eps = EPS_COEFF * p.anorm[qi] * p.gstat[0] + 1e-5f;
+  // the tensor-core pass tags the 6 low mantissa bits of a value with its column (score_tc.cuh):
+  // |tagged - untagged| <= 2^-17 |value|, bounded here by the largest magnitude in the window
+  const float amax = ptx::warp_max(valid ? fabsf(cv) : 0.f);
+  const float eps = EPS_COEFF * p.anorm[qi] * p.gstat[0] + 1e-5f + TAG_REL_ERR * amax;
   const float cutoff = a_k - 2.f * eps;                   // a_k = -inf when fewer than k candidates
   const bool in_S = valid && cv >= cutoff;
   const uint32_t smask = __ballot_sync(ptx::FULL_MASK, in_S);

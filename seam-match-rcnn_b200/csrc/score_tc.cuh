@@ -64,7 +64,7 @@ constexpr uint32_t NUM_BARS = 2 * NSTAGE + 2 + 8;
 constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;   // + slack for manual 1024-byte alignment
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-static_assert(OFF_CG % 16 == 0 && OFF_THRX % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+static_assert(OFF_CG % 16 == 0 && OFF_THRX % 16 == 0 && OFF_CMD % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
 struct Params {
   int Q, G, num_mtiles, ntiles_n;
@@ -75,9 +75,9 @@ struct Params {
   int mode;                   // 0 = normal; 1 = accumulators are drained unread (MMA-only ceiling)
   const float* cg;            // (G)
   uint32_t* thr_global;       // (Q) ordered-uint image of the per-row lower bound
-  uint32_t* rowcnt;           // (Q, P, 4) entries in each sub-list
+  uint32_t* rowcnt;           // (Q, P, 4) quad records in each sub-list
   uint32_t* rowflag;          // (Q) nonzero: the row lost candidates, must be ranked exhaustively
-  uint2* rowbuf;              // (Q, P, 4, CAP) {v, shard-local gallery row}
+  uint2* rowbuf;              // (Q, P, 4, CAP x 8 bytes) = CAP/2 quad records {w0,w1,w2,w3} per sub-list
   float* gmax;                // (Q, P, 4, 16) final group maxima of each thread (disjoint column groups)
   unsigned long long* cta_ns; // (grid, 2) optional: {duration in ns, segments} per CTA (developer diagnostics)
 };
@@ -166,28 +166,63 @@ __device__ __forceinline__ float eighth_largest_of_16(const float (&gm)[16]) {
   return r;
 }
 
-// v = acc + cg;  if (v > cmp) { *(uint2*)wp = {v, colbase + E}; wp += 8; }   -- predicated, no branch.
-// Only the low address word advances: a sub-list never straddles a 4 GiB boundary (power-of-two
-// size, aligned to it).
-template <int E>
-__device__ __forceinline__ float add_append(uint64_t& wp, uint32_t acc, float cg, float cmp, uint32_t colbase) {
-  float v;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b32 c, lo, hi;\n"
-      "add.f32 %1, %2, %3;\n"
-      "add.u32 c, %5, %6;\n"
-      "setp.gt.f32 p, %1, %4;\n"
-      "@p st.global.v2.b32 [%0], {%1, c};\n"
-      "mov.b64 {lo, hi}, %0;\n"
-      "@p add.u32 lo, lo, 8;\n"
-      "mov.b64 %0, {lo, hi};\n"
+// Candidate records.  Memory instructions are the expensive part of this epilogue (a store occupies
+// its scheduler's dispatch for several cycles even when every lane is predicated off), so candidates
+// are appended by QUADS of adjacent columns: one predicated 16-byte store per four accumulator elements,
+//   if (max(w0..w3) > cmp) { *wp = {w0,w1,w2,w3}; wp += 16; }            (no branch)
+// where w_e = (acc_e + cg_e) with the 6 low mantissa bits replaced by a tag: w0 carries the quad's
+// position q (0..15) inside the thread's 64-column quarter, w1..w3 carry 18 bits of the gallery tile
+// index, so a record names its four gallery rows by itself.  |w - v| <= 2^-17 |v| -- far inside the
+// fp16 operand error the re-score kernel allows for (it adds the term to its eps).  w is what is
+// compared and recorded as group maximum too: the whole filter is consistent in "w space".
+constexpr uint32_t TAG_MASK = 63u;
+constexpr int TAG_BITS = 6;
+template <int Q4>
+__device__ __forceinline__ float tagged_imm(uint32_t acc, float cg, uint32_t keep) {
+  float w;
+  asm("{\n"
+      ".reg .f32 v;\n"
+      "add.f32 v, %1, %2;\n"
+      "lop3.b32 %0, v, %3, %4, 0xEA;\n"      // (v & keep) | Q4
       "}\n"
-      : "+l"(wp), "=f"(v)
-      : "f"(__uint_as_float(acc)), "f"(cg), "f"(cmp), "r"(colbase), "n"(E)
-      : "memory");
-  return v;
+      : "=f"(w)
+      : "f"(__uint_as_float(acc)), "f"(cg), "r"(keep), "n"(Q4));
+  return w;
+}
+__device__ __forceinline__ float tagged_reg(uint32_t acc, float cg, uint32_t keep, uint32_t tag) {
+  float w;
+  asm("{\n"
+      ".reg .f32 v;\n"
+      "add.f32 v, %1, %2;\n"
+      "lop3.b32 %0, v, %3, %4, 0xEA;\n"
+      "}\n"
+      : "=f"(w)
+      : "f"(__uint_as_float(acc)), "f"(cg), "r"(keep), "r"(tag));
+  return w;
+}
+// Only the low address word advances: a sub-list never straddles a 4 GiB boundary (power-of-two size,
+// aligned to it).
+template <int VAR>
+__device__ __forceinline__ void append_quad(uint64_t& wp, float m, float cmp, float w0, float w1, float w2, float w3) {
+  if constexpr (VAR == 0) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 lo, hi;\n"
+        "setp.gt.f32 p, %1, %2;\n"
+        "@p st.global.v4.f32 [%0], {%3, %4, %5, %6};\n"
+        "mov.b64 {lo, hi}, %0;\n"
+        "@p add.u32 lo, lo, 16;\n"
+        "mov.b64 %0, {lo, hi};\n"
+        "}\n"
+        : "+l"(wp)
+        : "f"(m), "f"(cmp), "f"(w0), "f"(w1), "f"(w2), "f"(w3)
+        : "memory");
+  } else if constexpr (VAR == 2) {   // diagnostics: no store
+    asm volatile("{\n.reg .pred p;\n.reg .b32 lo, hi;\nsetp.gt.f32 p, %1, %2;\nmov.b64 {lo, hi}, %0;\n"
+                 "@p add.u32 lo, lo, 16;\nmov.b64 %0, {lo, hi};\n}\n"
+                 : "+l"(wp) : "f"(m), "f"(cmp) : "memory");
+  }
 }
 
 // ties the destination registers of an in-flight tcgen05.ld to the wait so the compiler
@@ -203,12 +238,15 @@ __device__ __forceinline__ void tmem_ld_wait_x32(uint32_t (&a)[32]) {
                : "memory");
 }
 
-// 16 accumulator columns of one row: + cg, append what beats cmp, fold into 8 of the 16 group
-// maxima (two columns per group and call; GOFF selects the half)
-template <int GOFF, int... E>
-__device__ __forceinline__ void filter16_impl(const uint32_t (&r)[16], const float* cgp, float (&gm)[GROUPS],
-                                              uint64_t& wp, float cmp, uint32_t col0,
-                                              std::integer_sequence<int, E...>) {
+// 16 accumulator columns of one row: + cg, tag, append the quads that beat cmp, fold the quad maxima
+// into 4 of the 16 group maxima (chunk c of a tile feeds groups 4c..4c+3: a group is 4 adjacent
+// columns of every tile, groups are pairwise disjoint)
+struct TileTags {
+  uint32_t t1, t2, t3;   // bits [0,6), [6,12), [12,18) of the gallery tile index
+};
+template <int VAR, int GOFF, int Q0>
+__device__ __forceinline__ void filter16(const uint32_t (&r)[16], const float* cgp, float (&gm)[GROUPS], uint64_t& wp,
+                                         float cmp, uint32_t keep, const TileTags& tg) {
   float cgv[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
@@ -218,17 +256,26 @@ __device__ __forceinline__ void filter16_impl(const uint32_t (&r)[16], const flo
     cgv[c4 * 4 + 2] = g4.z;
     cgv[c4 * 4 + 3] = g4.w;
   }
-  float v[16];
-  ((v[E] = add_append<E>(wp, r[E], cgv[E], cmp, col0)), ...);
+  float w[16];
+  w[0] = tagged_imm<Q0 + 0>(r[0], cgv[0], keep);
+  w[4] = tagged_imm<Q0 + 1>(r[4], cgv[4], keep);
+  w[8] = tagged_imm<Q0 + 2>(r[8], cgv[8], keep);
+  w[12] = tagged_imm<Q0 + 3>(r[12], cgv[12], keep);
 #pragma unroll
-  for (int g = 0; g < 8; ++g) gm[GOFF + g] = max3(gm[GOFF + g], v[g], v[g + 8]);
-}
-template <int GOFF>
-__device__ __forceinline__ void filter16(const uint32_t (&r)[16], const float* cgp, float (&gm)[GROUPS], uint64_t& wp,
-                                         float cmp, uint32_t col0) {
-  filter16_impl<GOFF>(r, cgp, gm, wp, cmp, col0, std::make_integer_sequence<int, 16>{});
+  for (int q = 0; q < 4; ++q) {
+    w[4 * q + 1] = tagged_reg(r[4 * q + 1], cgv[4 * q + 1], keep, tg.t1);
+    w[4 * q + 2] = tagged_reg(r[4 * q + 2], cgv[4 * q + 2], keep, tg.t2);
+    w[4 * q + 3] = tagged_reg(r[4 * q + 3], cgv[4 * q + 3], keep, tg.t3);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float m = fmaxf(max3(w[4 * q], w[4 * q + 1], w[4 * q + 2]), w[4 * q + 3]);
+    gm[GOFF + q] = fmaxf(gm[GOFF + q], m);
+    append_quad<VAR>(wp, m, cmp, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  }
 }
 
+template <int VAR>   // 0 = product; 2..4 = developer diagnostics (partial epilogues, wrong results)
 __global__ void __launch_bounds__(THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -406,7 +453,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int grow = 0, itile = 0;
     uint64_t wp = 0;
     uint32_t wlo_begin = 0;
-    const uint32_t room = (uint32_t)(p.CAP - QCOLS) * 8u;   // a list closes when < one tile's 64 entries fit
+    // a sub-list closes when another tile's worst case (16 quads) might not fit
+    const uint32_t room = (uint32_t)p.CAP * 8u - (uint32_t)(QCOLS / 4) * 16u;
+    // kept in a register (opaque to ptxas) so that the quad tag can be the LOP3's immediate operand
+    const uint32_t keep = ~TAG_MASK | (uint32_t)(p.Q >> 31);
     float thr = INFINITY;
     float gm[GROUPS];
     for (;;) {
@@ -421,8 +471,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         wp = reinterpret_cast<uint64_t>(p.rowbuf + li * (size_t)p.CAP);
         wlo_begin = (uint32_t)wp;            // only the low address word ever changes (no 4 GiB straddle)
         thr = row_ok ? ptx::ordered_to_float(__ldcg(p.thr_global + grow)) : INFINITY;
-        st = (row_ok ? ST_ROW : 0u) | (slot_ok ? ST_SLOT : ST_CLOSED) | ((row_ok && !slot_ok) ? ST_LOSSY : 0u) |
-             ((uint32_t)(cmd.w & 0xffff) << 8);
+        st = (row_ok ? ST_ROW : 0u) | (slot_ok ? ST_SLOT : (ST_CLOSED | ST_LOSSY)) | ((uint32_t)(cmd.w & 0xffff) << 8);
         itile = 0;
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) gm[g] = -INFINITY;
@@ -448,22 +497,25 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           st |= ST_CLOSED | ST_LOSSY;                                         // the row goes to the exhaustive path
         const float cmp = (seed || (st & ST_CLOSED)) ? INFINITY : thr;
         const float* cgp = cg_s + acc * BN + cq * QCOLS;
-        const uint32_t col0 = (uint32_t)(cmd.x * BN + cq * QCOLS);
+        TileTags tg;
+        tg.t1 = (uint32_t)cmd.x & TAG_MASK;
+        tg.t2 = ((uint32_t)cmd.x >> TAG_BITS) & TAG_MASK;
+        tg.t3 = ((uint32_t)cmd.x >> (2 * TAG_BITS)) & TAG_MASK;
         ptx::tmem_ld_wait_x16(ra);
         ptx::tmem_ld_x16(taddr + 16, rb);
-        filter16<0>(ra, cgp, gm, wp, cmp, col0);
+        filter16<VAR, 0, 0>(ra, cgp, gm, wp, cmp, keep, tg);
         ptx::tmem_ld_wait_x16(rb);
         ptx::tmem_ld_x16(taddr + 32, ra);
-        filter16<8>(rb, cgp + 16, gm, wp, cmp, col0 + 16);
+        filter16<VAR, 4, 4>(rb, cgp + 16, gm, wp, cmp, keep, tg);
         ptx::tmem_ld_wait_x16(ra);
         ptx::tmem_ld_x16(taddr + 48, rb);
-        filter16<0>(ra, cgp + 32, gm, wp, cmp, col0 + 32);
+        filter16<VAR, 8, 8>(ra, cgp + 32, gm, wp, cmp, keep, tg);
         ptx::tmem_ld_wait_x16(rb);
         // this warp's accumulator columns have all been read: hand the TMEM slot back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
-        filter16<8>(rb, cgp + 48, gm, wp, cmp, col0 + 48);
+        filter16<VAR, 12, 12>(rb, cgp + 48, gm, wp, cmp, keep, tg);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&cg_empty[acc]);
         // share the bound: each of the row's 4 threads vouches for 8 distinct items at or above the
@@ -487,7 +539,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if ((cmd.y & CMD_SEG_END) && (st & ST_ROW)) {
           if (st & ST_SLOT) {
             const size_t li = ((size_t)grow * p.P + (st >> 8)) * NQ + cq;
-            p.rowcnt[li] = ((uint32_t)wp - wlo_begin) >> 3;
+            p.rowcnt[li] = ((uint32_t)wp - wlo_begin) >> 4;   // quads
             float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
             gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
             gd[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);

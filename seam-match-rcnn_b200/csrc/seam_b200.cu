@@ -170,8 +170,11 @@ int seam_create(seam_handle** out, int device) {
   }
   h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   // opt in to large dynamic shared memory once
-  cudaFuncSetAttribute(score::score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(score::score_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)score::SMEM_BYTES);
+  cudaFuncSetAttribute(score::score_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
+  cudaFuncSetAttribute(score::score_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
+  cudaFuncSetAttribute(score::score_topk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)aggw::smem_bytes<4>());
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -445,27 +448,29 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
   if (segs > s.grid) segs = s.grid;
   s.P = (int)segs;
   s.nseed = env_int("SEAM_SCORE_NSEED", 2);
-  // expected appends of one epilogue thread over a piece of T tiles (64 columns each): with a
-  // cold bound the first tile is appended whole and tile t adds ~32/t (about 130 items sit above
-  // a row's 32-group bound, a quarter of them in this thread's columns); seeded pieces start at
-  // the rate of tile nseed+1.
-  // Segments shorter than 4*nseed tiles run unseeded and may append whole tiles.
+  // Expected bytes one epilogue thread appends over a piece of T tiles.  A record is a quad of 4 adjacent
+  // columns (16 bytes), appended when its maximum beats the row's bound: with a cold bound a whole tile
+  // (16 quads) goes out, later about 32/t items per tile t (about 130 items sit above a row's 32-group
+  // bound, a quarter of them in this thread's columns), nearly all in different quads; seeded pieces start
+  // at the rate of tile nseed+1.  Segments shorter than 4*nseed tiles run unseeded and may append whole
+  // tiles.  3x margin on the sparse part.
   const double T = (double)(max_range < s.ntiles_n ? max_range : s.ntiles_n);
+  const double tile_bytes = score::QCOLS / 4 * 16.0;
   double need;
   if (s.nseed > 0) {
     const double short_tiles = T < 4.0 * s.nseed - 1.0 ? T : 4.0 * s.nseed - 1.0;
-    need = short_tiles * score::QCOLS;
+    need = short_tiles * tile_bytes;
     if (T >= 4.0 * s.nseed) {
-      const double seeded = 3.0 * (16.0 + 32.0 * log((T + s.nseed) / s.nseed));
+      const double seeded = 16.0 * 3.0 * (16.0 + 32.0 * log((T + s.nseed) / s.nseed));
       if (seeded > need) need = seeded;
     }
   } else {
-    need = 3.0 * (64.0 + 32.0 * log(T));
+    need = 16.0 * 3.0 * (64.0 + 32.0 * log(T));
   }
-  if (need > T * score::QCOLS) need = T * score::QCOLS;      // a thread cannot append more than it sees
-  need += score::QCOLS;                                      // a list closes one tile before it is full
-  int cap = 2 * score::QCOLS;                                // power of two: a sub-list is aligned to its size
-  while (cap < (int)need && cap < 8192) cap *= 2;
+  if (need > T * tile_bytes) need = T * tile_bytes;          // a thread cannot append more than it sees
+  need += tile_bytes;                                        // a list closes one tile before it is full
+  int cap = 2 * score::QCOLS;                                // 8-byte units; power of two: a sub-list is aligned to its size
+  while (cap * 8 < (int)need && cap < 8192) cap *= 2;
   s.CAP = cap;
   const size_t nlists = (size_t)s.P * score::NQ;
   size_t o = 0;
@@ -542,6 +547,8 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   if (!aligned16(q) || !aligned16(g) || !aligned16(g16) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_topk: q/g/g16 need 16-byte, workspace 256-byte alignment");
   const ScorePlan s = plan_score(h->num_sms, Q, G);
+  if (s.ntiles_n > (1 << 18))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_topk: G=%d exceeds the 2^26 gallery rows one shard may hold", G);
   if (workspace_bytes < s.total)
     return fail(h, SEAM_ERR_STATE, "seam_score_topk: workspace too small (%zu < %zu)", workspace_bytes, s.total);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -591,7 +598,10 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
                   : nullptr;
   {
     ProfileScope prof(h, SEAM_KERNEL_SCORE, stream);
-    score::score_topk_kernel<<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    if (sp.mode == 2) score::score_topk_kernel<2><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    else if (sp.mode == 3) score::score_topk_kernel<3><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    else if (sp.mode == 4) score::score_topk_kernel<4><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    else score::score_topk_kernel<0><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     SEAM_LAUNCHED(h, "score_topk_kernel");
   }
 

@@ -53,10 +53,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // error the host reports) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+  uint64_t t0 = 0;
+  for (;;) {
+    // the inner loop is the one that shares a scheduler with working warps: keep it to the try_wait
+    // (which itself suspends the warp for a while), a counter and the branch
+#pragma unroll 1
+    for (int spins = 0; spins < 4096; ++spins)
+      if (mbar_try_wait(bar, parity)) return;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) __trap();
   }
 }
 
@@ -177,6 +183,16 @@ __device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&r)[16]) {
 }
 
 // ----------------------------------------------------------------------------- misc
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
