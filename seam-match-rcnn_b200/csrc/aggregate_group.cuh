@@ -42,8 +42,13 @@ struct Smem {
 };
 
 using aggw::Params;
-using aggw::dot4;
-using aggw::fma4;
+using aggw::Vec8;
+using aggw::dot8;
+using aggw::fma8;
+using aggw::load_vec8;
+using aggw::zero_vec8;
+using aggw::unpack_vec8;
+using aggw::pk;
 using ptx::treduce;
 
 template <int GW>
@@ -102,14 +107,10 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_group_kernel(const Param
   };
 
   const float* fold = p.fold;
-  const float4 ut0 = *reinterpret_cast<const float4*>(fold + Fold::U_THETA + 4 * lane);
-  const float4 ut1 = *reinterpret_cast<const float4*>(fold + Fold::U_THETA + 128 + 4 * lane);
-  const float4 up0 = *reinterpret_cast<const float4*>(fold + Fold::U_PHI + 4 * lane);
-  const float4 up1 = *reinterpret_cast<const float4*>(fold + Fold::U_PHI + 128 + 4 * lane);
-  const float4 ug0 = *reinterpret_cast<const float4*>(fold + Fold::U_G + 4 * lane);
-  const float4 ug1 = *reinterpret_cast<const float4*>(fold + Fold::U_G + 128 + 4 * lane);
-  const float4 wa0 = *reinterpret_cast<const float4*>(fold + Fold::W_A + 4 * lane);
-  const float4 wa1 = *reinterpret_cast<const float4*>(fold + Fold::W_A + 128 + 4 * lane);
+  const Vec8 ut = load_vec8(fold + Fold::U_THETA, lane);
+  const Vec8 up = load_vec8(fold + Fold::U_PHI, lane);
+  const Vec8 ug = load_vec8(fold + Fold::U_G, lane);
+  const Vec8 wa = load_vec8(fold + Fold::W_A, lane);
   const float c_s = fold[Fold::CONSTS + 3];
   // scalar layout per frame: [a, d, b, c]; constants c_theta, 0, c_phi, c_g
   const int comp = lane & 3;
@@ -125,21 +126,16 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_group_kernel(const Param
     const int nw = max(0, min(len - FB * wg, FB));
 
     // ---- my 16 frames -> registers, four dots per frame
-    float4 x0[FB], x1[FB];
+    Vec8 x[FB];
     float acc[32], acc2[32];
 #pragma unroll
     for (int t = 0; t < FB; ++t) {
-      if (t < nw) {
-        x0[t] = *reinterpret_cast<const float4*>(xs + t * D + 4 * lane);
-        x1[t] = *reinterpret_cast<const float4*>(xs + t * D + 128 + 4 * lane);
-      } else {
-        x0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        x1[t] = x0[t];
-      }
-      const float va = dot4(x0[t], ut0) + dot4(x1[t], ut1);
-      const float vd = dot4(x0[t], wa0) + dot4(x1[t], wa1);
-      const float vb = dot4(x0[t], up0) + dot4(x1[t], up1);
-      const float vc = dot4(x0[t], ug0) + dot4(x1[t], ug1);
+      if (t < nw) x[t] = load_vec8(xs + t * D, lane);
+      else x[t] = zero_vec8();
+      const float va = dot8(x[t], ut);
+      const float vd = dot8(x[t], wa);
+      const float vb = dot8(x[t], up);
+      const float vc = dot8(x[t], ug);
       if (t < 8) {
         acc[4 * t + 0] = va;
         acc[4 * t + 1] = vd;
@@ -209,18 +205,19 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_group_kernel(const Param
     const float qsum_w = ptx::warp_sum(half == 0 ? q_j : 0.f);
 
     // ---- partial weighted sums over my frames, 8 channels per lane
-    float4 po0 = make_float4(0.f, 0.f, 0.f, 0.f), po1 = po0, r0 = po0, r1 = po0;
+    Vec8 pov = zero_vec8(), rv = zero_vec8();
 #pragma unroll
     for (int t = 0; t < FB; ++t) {
       const float pt = __shfl_sync(ptx::FULL_MASK, p_t, t);
       const float qt = __shfl_sync(ptx::FULL_MASK, q_j, t);
       if (t < nw) {
-        fma4(po0, pt, x0[t]);
-        fma4(po1, pt, x1[t]);
-        fma4(r0, qt, x0[t]);
-        fma4(r1, qt, x1[t]);
+        fma8(pov, pk(pt, pt), x[t]);
+        fma8(rv, pk(qt, qt), x[t]);
       }
     }
+    float4 po0, po1, r0, r1;
+    unpack_vec8(pov, po0, po1);
+    unpack_vec8(rv, r0, r1);
     {
       float* pw = &gs.part[wg][0];
       *reinterpret_cast<float4*>(pw + 4 * lane) = po0;

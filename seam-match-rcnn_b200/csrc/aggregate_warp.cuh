@@ -60,14 +60,59 @@ constexpr size_t smem_bytes() {
 
 using ptx::treduce;
 
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+// Packed fp32 pairs (FFMA2 / FMUL2 on sm_100a): the kernels here are bound by instruction issue, not by
+// the fp32 pipe, and a pair instruction does the work of two in one issue slot.  A lane's 8 channels
+// of a frame are two 16-byte shared-memory loads = four pairs.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-__device__ __forceinline__ void fma4(float4& acc, float s, const float4& x) {
-  acc.x = fmaf(s, x.x, acc.x);
-  acc.y = fmaf(s, x.y, acc.y);
-  acc.z = fmaf(s, x.z, acc.z);
-  acc.w = fmaf(s, x.w, acc.w);
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+struct Vec8 {   // this lane's channels [4l,4l+4) and [128+4l,128+4l+4) as four pairs
+  u64 a, b, c, d;
+};
+__device__ __forceinline__ Vec8 load_vec8(const float* row, int lane) {
+  const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(row + 4 * lane);
+  const ulonglong2 hi = *reinterpret_cast<const ulonglong2*>(row + 128 + 4 * lane);
+  return Vec8{lo.x, lo.y, hi.x, hi.y};
+}
+__device__ __forceinline__ Vec8 zero_vec8() { return Vec8{0ull, 0ull, 0ull, 0ull}; }
+// x . u over the lane's 8 channels
+__device__ __forceinline__ float dot8(const Vec8& x, const Vec8& u) {
+  u64 acc = mul2(x.a, u.a);
+  acc = fma2(x.b, u.b, acc);
+  acc = fma2(x.c, u.c, acc);
+  acc = fma2(x.d, u.d, acc);
+  float lo, hi;
+  upk(acc, lo, hi);
+  return lo + hi;
+}
+// acc += s * x   (ss = {s, s})
+__device__ __forceinline__ void fma8(Vec8& acc, u64 ss, const Vec8& x) {
+  acc.a = fma2(ss, x.a, acc.a);
+  acc.b = fma2(ss, x.b, acc.b);
+  acc.c = fma2(ss, x.c, acc.c);
+  acc.d = fma2(ss, x.d, acc.d);
+}
+__device__ __forceinline__ void unpack_vec8(const Vec8& v, float4& lo, float4& hi) {
+  upk(v.a, lo.x, lo.y);
+  upk(v.b, lo.z, lo.w);
+  upk(v.c, hi.x, hi.y);
+  upk(v.d, hi.z, hi.w);
 }
 // tf32-exact split: hi keeps the 10 explicit mantissa bits the tensor core reads, lo the rest
 __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
@@ -133,14 +178,10 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
 
   // folded vectors at this lane's two float4 positions
   const float* fold = p.fold;
-  const float4 ut0 = *reinterpret_cast<const float4*>(fold + Fold::U_THETA + 4 * lane);
-  const float4 ut1 = *reinterpret_cast<const float4*>(fold + Fold::U_THETA + 128 + 4 * lane);
-  const float4 up0 = *reinterpret_cast<const float4*>(fold + Fold::U_PHI + 4 * lane);
-  const float4 up1 = *reinterpret_cast<const float4*>(fold + Fold::U_PHI + 128 + 4 * lane);
-  const float4 ug0 = *reinterpret_cast<const float4*>(fold + Fold::U_G + 4 * lane);
-  const float4 ug1 = *reinterpret_cast<const float4*>(fold + Fold::U_G + 128 + 4 * lane);
-  const float4 wa0 = *reinterpret_cast<const float4*>(fold + Fold::W_A + 4 * lane);
-  const float4 wa1 = *reinterpret_cast<const float4*>(fold + Fold::W_A + 128 + 4 * lane);
+  const Vec8 ut = load_vec8(fold + Fold::U_THETA, lane);
+  const Vec8 up = load_vec8(fold + Fold::U_PHI, lane);
+  const Vec8 ug = load_vec8(fold + Fold::U_G, lane);
+  const Vec8 wa = load_vec8(fold + Fold::W_A, lane);
   const float c_s = fold[Fold::CONSTS + 3];
   // scalar layout per frame: [a, d, b, c]; constants c_theta, 0, c_phi, c_g
   const int comp = lane & 3;
@@ -170,7 +211,7 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
     auto process = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
       // ---- frames -> registers, four dots per frame
-      float4 x0[TR], x1[TR];
+      Vec8 x[TR];
       constexpr int N1 = NV <= 16 ? 16 : 32;                       // first butterfly: frames 0..7
       constexpr int N2 = NV <= 32 ? 1 : (NV - 32 <= 8 ? 8 : 32);    // second butterfly: frames 8..
       float acc[N1], acc2[N2];
@@ -180,17 +221,12 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
       for (int i = 0; i < N2; ++i) acc2[i] = 0.f;
   #pragma unroll
       for (int t = 0; t < TR; ++t) {
-        if (FULL || t < len) {
-          x0[t] = *reinterpret_cast<const float4*>(xs + t * D + 4 * lane);
-          x1[t] = *reinterpret_cast<const float4*>(xs + t * D + 128 + 4 * lane);
-        } else {
-          x0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-          x1[t] = x0[t];
-        }
-        const float va = dot4(x0[t], ut0) + dot4(x1[t], ut1);
-        const float vd = dot4(x0[t], wa0) + dot4(x1[t], wa1);
-        const float vb = dot4(x0[t], up0) + dot4(x1[t], up1);
-        const float vc = dot4(x0[t], ug0) + dot4(x1[t], ug1);
+        if (FULL || t < len) x[t] = load_vec8(xs + t * D, lane);
+        else x[t] = zero_vec8();
+        const float va = dot8(x[t], ut);
+        const float vd = dot8(x[t], wa);
+        const float vb = dot8(x[t], up);
+        const float vc = dot8(x[t], ug);
         if (4 * t < 32) {
           acc[4 * t + 0] = va;
           acc[4 * t + 1] = vd;
@@ -258,23 +294,25 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
           q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
         }
       }
-      if (lane < TR) scal[4 * lane + 3] = q_j;
       const float qsum = ptx::warp_sum(q_j);
+      __syncwarp();                                    // all lanes have read the a_t
+      if (lane < TR) *reinterpret_cast<float4*>(scal + 4 * lane) = make_float4(p_t, p_t, q_j, q_j);
       if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
       __syncwarp();
 
       // ---- weighted sums over frames, 8 channels per lane
-      float4 po0 = make_float4(0.f, 0.f, 0.f, 0.f), po1 = po0, r0 = po0, r1 = po0;
+      Vec8 pov = zero_vec8(), rv = zero_vec8();
   #pragma unroll
       for (int t = 0; t < TR; ++t) {
         if (FULL || t < len) {
-          const float2 pq = *reinterpret_cast<const float2*>(scal + 4 * t + 2);
-          fma4(po0, pq.x, x0[t]);
-          fma4(po1, pq.x, x1[t]);
-          fma4(r0, pq.y, x0[t]);
-          fma4(r1, pq.y, x1[t]);
+          const ulonglong2 pq = *reinterpret_cast<const ulonglong2*>(scal + 4 * t);   // {p,p}, {q,q}
+          fma8(pov, pq.x, x[t]);
+          fma8(rv, pq.y, x[t]);
         }
       }
+      float4 po0, po1, r0, r1;
+      unpack_vec8(pov, po0, po1);
+      unpack_vec8(rv, r0, r1);
       if (FULL ? TR > 1 : len > 1) {
         const float4 wbg0 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 4 * lane);
         const float4 wbg1 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 128 + 4 * lane);
