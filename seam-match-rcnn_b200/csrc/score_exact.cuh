@@ -38,19 +38,37 @@ __device__ __forceinline__ Slice load_slice(const float* row, int lane) {
   s.hi = *reinterpret_cast<const float4*>(row + 128 + 4 * lane);
   return s;
 }
+// Packed fp32 pairs (sub/mul/fma .f32x2 = one issue slot for two IEEE fp32 operations: every kernel
+// here is bound by instruction issue).  Each lane forms two partial sums per logit (even / odd
+// channels of its slice) and adds them at the end.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float sum2(u64 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
 __device__ __forceinline__ void sqdiff_dot2(const Slice& q, const Slice& g, const Slice& w0, const Slice& w1,
                                             float& p0, float& p1) {
-  float d, s;
-  p0 = 0.f;
-  p1 = 0.f;
-#define SEAM_TERM(F)        \
-  d = q.F - g.F;            \
-  s = d * d;                \
-  p0 = fmaf(w0.F, s, p0);   \
-  p1 = fmaf(w1.F, s, p1);
-  SEAM_TERM(lo.x) SEAM_TERM(lo.y) SEAM_TERM(lo.z) SEAM_TERM(lo.w)
-  SEAM_TERM(hi.x) SEAM_TERM(hi.y) SEAM_TERM(hi.z) SEAM_TERM(hi.w)
-#undef SEAM_TERM
+  u64 a0, a1, d, s;
+#define SEAM_TERM2(F, X, Y, FIRST)                                                                   \
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(q.F.X, q.F.Y)), "l"(pk2(g.F.X, g.F.Y)));      \
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(s) : "l"(d));                                               \
+  if (FIRST) {                                                                                       \
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a0) : "l"(pk2(w0.F.X, w0.F.Y)), "l"(s));                  \
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a1) : "l"(pk2(w1.F.X, w1.F.Y)), "l"(s));                  \
+  } else {                                                                                           \
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(pk2(w0.F.X, w0.F.Y)), "l"(s));              \
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(pk2(w1.F.X, w1.F.Y)), "l"(s));              \
+  }
+  SEAM_TERM2(lo, x, y, true) SEAM_TERM2(lo, z, w, false) SEAM_TERM2(hi, x, y, false) SEAM_TERM2(hi, z, w, false)
+#undef SEAM_TERM2
+  p0 = sum2(a0);
+  p1 = sum2(a1);
 }
 // both logits of one pair, all lanes get the result
 __device__ __forceinline__ void pair_logits(const Slice& q, const float* grow, const Slice& w0, const Slice& w1,
@@ -223,9 +241,11 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   // they are swept four at a time with eight loads per lane in flight.
   float cut = tau;                                 // max(tau, 32nd best so far); entries equal to tau pass
   bool cut_strict = false;
+  // one compare per value: v passes iff v > cut_lo, cut_lo = cut (strict) or the next float below it
+  float cut_lo = tau > -INFINITY ? nextafterf(tau, -INFINITY) : -INFINITY;
   {
     // A tighter start: the row's group maxima belong to pairwise distinct gallery items, so the
-    // 32nd largest of them (here: its ordered-integer image to 10 significant bits, found MSB
+    // 32nd largest of them (here: its ordered-integer image to 8 significant bits, found MSB
     // first) also bounds the 32nd best -- with ~40 instead of ~300 items above it.
     const int nval = p.nlists * 16;
     const float* gmp = p.gmax + (size_t)qi * nval;
@@ -247,16 +267,20 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
       if (hi != lo) {
         const int b0 = 31 - __clz(hi ^ lo);
         K = hi & ~((2u << b0) - 1u);                  // common prefix; at least 32 keys are >= it
-        for (int b = b0; b >= 0 && b > b0 - 10; --b) {
+        for (int b = b0; b >= 0 && b > b0 - 8; --b) {
           const uint32_t T = K | (1u << b);
-          int c = 0;
+          uint32_t c = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) c += key[j] >= T;
-          if (__reduce_add_sync(ptx::FULL_MASK, c) >= 32) K = T;
+          for (int j = 0; j < 8; ++j)
+            asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p add.u32 %0, %0, 1;\n}\n" : "+r"(c) : "r"(key[j]), "r"(T));
+          if (__reduce_add_sync(ptx::FULL_MASK, c) >= 32u) K = T;
         }
       }
       const float tt = ptx::ordered_to_float(K);
-      if (K != 0 && tt > cut) cut = tt;              // K == 0: fewer than 32 finite maxima
+      if (K != 0 && tt > cut) {                      // K == 0: fewer than 32 finite maxima
+        cut = tt;
+        cut_lo = nextafterf(tt, -INFINITY);
+      }
     }
   }
   // A record is a quad {w0,w1,w2,w3} of adjacent gallery rows (score_tc.cuh): the 6 low mantissa bits of
@@ -281,7 +305,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
 #pragma unroll
     for (int el = 0; el < 4; ++el) {
       const float ev = __uint_as_float(wv[el]);
-      const bool pass = have && (cut_strict ? ev > cut : ev >= cut);
+      const bool pass = have && ev > cut_lo;
       const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
       if (mask == 0u) continue;                      // warp-uniform
       if (pass) wb[fill + __popc(mask & ((1u << lane) - 1u))] = make_uint2(wv[el], col + el);
@@ -297,6 +321,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
       if (worst > cut || (worst == cut && worst > -INFINITY)) {
         cut = worst;
         cut_strict = true;                           // ties with the 32nd best cannot displace it
+        cut_lo = worst;
       }
     }
     __syncwarp();
@@ -308,36 +333,34 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
       certified = false;
       break;
     }
-    const int nl = min(32, p.nlists - l0);
+    const int nl = min(32, p.nlists - l0);            // a multiple of RS_SUBL = 4 (4 sub-lists per piece)
     for (int j0 = 0; j0 < nl; j0 += RS_SUBL) {       // RS_SUBL sub-lists per round, 32 quads of each
-      int n8[RS_SUBL];
-      const uint4* buf8[RS_SUBL];
+      int n4[RS_SUBL];
       int nmax = 0;
 #pragma unroll
       for (int u = 0; u < RS_SUBL; ++u) {
-        const int n_u = (int)__shfl_sync(ptx::FULL_MASK, my_n, min(j0 + u, 31));
-        n8[u] = j0 + u < nl ? n_u : 0;
-        buf8[u] = rowq + (size_t)(l0 + min(j0 + u, nl - 1)) * capq;
-        nmax = max(nmax, n8[u]);
+        n4[u] = (int)__shfl_sync(ptx::FULL_MASK, my_n, j0 + u);
+        nmax = max(nmax, n4[u]);
       }
+      const uint4* lp = rowq + (size_t)(l0 + j0) * capq + lane;
       for (int base = 0; base < nmax; base += 32) {
         uint4 e[RS_SUBL];
 #pragma unroll
-        for (int u = 0; u < RS_SUBL; ++u)
-          e[u] = base + lane < n8[u] ? __ldcs(buf8[u] + base + lane) : make_uint4(0u, 0u, 0u, 0u);
+        for (int u = 0; u < RS_SUBL; ++u)             // slots past a list's end read as -inf: never pass
+          e[u] = base + lane < n4[u] ? __ldcs(lp + (size_t)u * capq + base)
+                                     : make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
 #pragma unroll
         for (int u = 0; u < RS_SUBL; ++u) {
-          if (n8[u] <= base) continue;               // warp-uniform
           const float m = fmaxf(fmaxf(__uint_as_float(e[u].x), __uint_as_float(e[u].y)),
                                 fmaxf(__uint_as_float(e[u].z), __uint_as_float(e[u].w)));
-          const bool pass = base + lane < n8[u] && (cut_strict ? m > cut : m >= cut);
+          const bool pass = m > cut_lo;
           const uint32_t mask = __ballot_sync(ptx::FULL_MASK, pass);
-          if (mask == 0u) continue;
+          if (mask == 0u) continue;                  // warp-uniform
           if (pass) {
             const uint32_t tile = (e[u].y & 63u) | ((e[u].z & 63u) << 6) | ((e[u].w & 63u) << 12);
             const int pos = qfill + __popc(mask & ((1u << lane) - 1u));
             qb[pos] = e[u];
-            qc[pos] = tile * 256u + (uint32_t)((l0 + j0 + u) & 3) * 64u + (e[u].x & 63u) * 4u;
+            qc[pos] = tile * 256u + (uint32_t)((j0 + u) & 3) * 64u + (e[u].x & 63u) * 4u;
           }
           qfill += __popc(mask);
           if (qfill >= 32) {
