@@ -6,7 +6,7 @@ import seam_match_rcnn_b200 as pkg
 from bench import random_init_weights
 dev = torch.device("cuda:0")
 e = pkg.SeamEngine(dev); e.load_weights(random_init_weights(dev))
-Q, G = 15000, 15000
+Q, G = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (15000, 15000)
 torch.manual_seed(0)
 q = torch.randn(Q, 256, device=dev); g = torch.randn(G, 256, device=dev)
 gal = e.prepare_gallery(g)
@@ -14,7 +14,8 @@ for _ in range(3): e.score_topk(q, gal, 20)
 torch.cuda.synchronize()
 plan = e.score_plan(Q, G); ws = e._ws["score"]
 off = plan["off_rows"] + ((Q * 4 - 4096) & ~7)
-t = ws[off:off + 148 * 16].view(torch.int64).view(148, 2).cpu()
+nc = plan['ctas']
+t = ws[off:off + nc * 16].view(torch.int64).view(nc, 2).cpu()
 ns, seg = t[:, 0].float() / 1e3, t[:, 1]
 print("per-CTA us: min %.1f mean %.1f max %.1f" % (ns.min(), ns.mean(), ns.max()))
 for sgc in sorted(set(seg.tolist())):

@@ -22,8 +22,8 @@
 // threshold-only mode.
 //
 // Work decomposition: the (query tile, gallery tile) grid is linearised query-major and cut
-// into one contiguous, equally long range per CTA; a range is processed as at most a few
-// "segments" (one query tile x a run of gallery tiles).
+// into one contiguous range per CTA, balanced on the host by cost (tiles + sample tiles + segment
+// starts); a range is processed as at most a few "segments" (one query tile x a run of gallery tiles).
 //
 // Roles (608 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
 // allocator, then stages cg tiles, warps 3..18 = epilogue (warp%4 selects the TMEM lane quarter =
@@ -66,6 +66,7 @@ constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;   // + slack for manual 10
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 static_assert(OFF_CG % 16 == 0 && OFF_THRX % 16 == 0 && OFF_CMD % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
+constexpr int MAX_GRID = 160;          // one persistent CTA per SM
 struct Params {
   int Q, G, num_mtiles, ntiles_n;
   long long total_tiles;
@@ -80,16 +81,18 @@ struct Params {
   uint2* rowbuf;              // (Q, P, 4, CAP x 8 bytes) = CAP/2 quad records {w0,w1,w2,w3} per sub-list
   float* gmax;                // (Q, P, 4, 16) final group maxima of each thread (disjoint column groups)
   unsigned long long* cta_ns; // (grid, 2) optional: {duration in ns, segments} per CTA (developer diagnostics)
+  int tb[MAX_GRID + 1];       // CTA b sweeps the linearised tiles [tb[b], tb[b+1]) (cost-balanced on the host)
 };
 
-// contiguous tile range of CTA b out of nb
-__device__ __forceinline__ void cta_range(long long total, int nb, int b, long long& t0, long long& t1) {
-  t0 = total * b / nb;
-  t1 = total * (b + 1) / nb;
-}
-// the CTA whose range contains tile t
-__device__ __forceinline__ int cta_of_tile(long long total, int nb, long long t) {
-  return (int)(((t + 1) * nb + total - 1) / total) - 1;
+// the CTA whose (non-empty) range contains tile t: the largest b with tb[b] <= t
+__device__ __forceinline__ int cta_of_tile(const Params& p, int nb, long long t) {
+  int lo = 0, hi = nb - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)p.tb[mid] <= t) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
 }
 
 // One segment = query tile m, gallery tiles [nt0, nt0 + n_main), preceded by n_seed sample tiles
@@ -204,7 +207,7 @@ __device__ __forceinline__ float tagged_reg(uint32_t acc, float cg, uint32_t kee
 // aligned to it).
 template <int VAR>
 __device__ __forceinline__ void append_quad(uint64_t& wp, float m, float cmp, float w0, float w1, float w2, float w3) {
-  if constexpr (VAR == 0) {
+  if constexpr (VAR == 0 || VAR == 5) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -250,6 +253,10 @@ __device__ __forceinline__ void filter16(const uint32_t (&r)[16], const float* c
   float cgv[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
+    if constexpr (VAR == 5) {   // diagnostics: no column term
+      cgv[c4 * 4 + 0] = cgv[c4 * 4 + 1] = cgv[c4 * 4 + 2] = cgv[c4 * 4 + 3] = -0.f;
+      continue;
+    }
     const float4 g4 = *reinterpret_cast<const float4*>(cgp + c4 * 4);
     cgv[c4 * 4 + 0] = g4.x;
     cgv[c4 * 4 + 1] = g4.y;
@@ -328,7 +335,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_s;
 
   long long t_begin, t_end;
-  cta_range(p.total_tiles, gridDim.x, blockIdx.x, t_begin, t_end);
+  t_begin = p.tb[blockIdx.x];
+  t_end = p.tb[blockIdx.x + 1];
   const uint64_t dbg_t0 = p.cta_ns ? ptx::globaltimer_ns() : 0;
 
   if (warp == 0) {
@@ -409,7 +417,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     while (t < t_end) {
       const Segment sg = segment_at(p, t_begin, t, t_end, next);
       const int n = sg.count();
-      const int piece = blockIdx.x - cta_of_tile(p.total_tiles, gridDim.x, (long long)sg.m * p.ntiles_n);
+      const int piece = blockIdx.x - cta_of_tile(p, gridDim.x, (long long)sg.m * p.ntiles_n);
       for (int i = 0; i < n; ++i) {
         const int nt = sg.tile(i);
         const int j0 = nt * BN + lane * 8;

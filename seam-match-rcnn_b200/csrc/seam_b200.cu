@@ -175,6 +175,7 @@ int seam_create(seam_handle** out, int device) {
   cudaFuncSetAttribute(score::score_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(score::score_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(score::score_topk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
+  cudaFuncSetAttribute(score::score_topk_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)aggw::smem_bytes<4>());
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -417,6 +418,7 @@ int seam_prepare_gallery(seam_handle* h, const float* g, int G, void* g16, float
 
 struct ScorePlan {
   int num_mtiles, ntiles_n, grid, P, CAP, nseed;
+  int tb[score::MAX_GRID + 1];
   long long total_tiles;
   size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_gmax, off_rowflag, off_rowbuf, off_cnt, off_rows, total;
 };
@@ -442,12 +444,70 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
     const int cap_grid = env_int("SEAM_DEBUG_SCORE_GRID", 0);   // developer diagnostics only
     if (cap_grid > 0 && cap_grid < s.grid) s.grid = cap_grid;
   }
-  const long long min_range = s.total_tiles / s.grid;           // shortest per-CTA range (>= 1)
-  const long long max_range = (s.total_tiles + s.grid - 1) / s.grid;
-  long long segs = (s.ntiles_n + min_range - 1) / min_range + 1;
-  if (segs > s.grid) segs = s.grid;
-  s.P = (int)segs;
-  s.nseed = env_int("SEAM_SCORE_NSEED", 2);
+  if (s.grid > score::MAX_GRID) s.grid = score::MAX_GRID;
+  s.nseed = env_int("SEAM_SCORE_NSEED", 4);
+  // Cost-balanced contiguous ranges.  A tile costs 1; a segment start costs SEG_COST (query tile load,
+  // epilogue hand-over) plus, when it lies within the CTA's first WARM_TILES tiles (score_tc.cuh), its
+  // min(nseed, length) threshold-only sample tiles.  walk() cuts ranges of cost <= target; the smallest
+  // target whose last range also fits is found by bisection.
+  const double SEG_COST = 0.35;
+  const long long ntn = s.ntiles_n, total = s.total_tiles;
+  auto walk = [&](double target, int* tb) -> double {   // returns the cost of the last CTA's range
+    long long pos = 0;
+    tb[0] = 0;
+    for (int b = 0; b < s.grid; ++b) {
+      const long long t0 = pos;
+      double cost = 0.0;
+      const bool last = b == s.grid - 1;
+      while (pos < total) {
+        const long long row_end = (pos / ntn + 1) * ntn;
+        const long long seg_len = row_end - pos;
+        const bool cold = pos - t0 < score::WARM_TILES;
+        // sample tiles if the whole rest of the row were taken; a shorter cut samples at most as many
+        const double over = SEG_COST + (cold ? (double)(seg_len < s.nseed ? seg_len : s.nseed) : 0.0);
+        long long n = seg_len;
+        if (!last) {
+          const double room = target - cost - over;
+          if (room < 1.0 && pos > t0) break;             // not worth starting another segment
+          const long long fit = room < 1.0 ? 1 : (long long)room;
+          if (fit < n) n = fit;
+        }
+        cost += over + (double)n;
+        pos += n;
+        if (pos < row_end) break;                        // budget exhausted inside the row
+      }
+      tb[b + 1] = (int)pos;
+      if (last) return cost;
+    }
+    return 0.0;
+  };
+  {
+    double lo = (double)total / s.grid, hi = (double)total / s.grid + 3.0 * (s.nseed + 1) + 2.0;
+    for (int it = 0; it < 40; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (walk(mid, s.tb) <= mid) hi = mid;
+      else lo = mid;
+    }
+    walk(hi, s.tb);
+    s.tb[s.grid] = (int)total;
+  }
+  // sub-list slots per row = most CTAs whose ranges touch one query tile's sweep (pieces are numbered
+  // from the first CTA that touches the row)
+  int pmax = 1;
+  long long max_range = 1;
+  {
+    int b_first = 0;
+    for (long long m = 0; m < s.num_mtiles; ++m) {
+      const long long r0 = m * ntn, r1 = r0 + ntn;
+      while (b_first + 1 < s.grid && s.tb[b_first + 1] <= r0) ++b_first;   // first CTA with tb[b+1] > r0
+      int b_last = b_first;
+      while (b_last + 1 < s.grid && s.tb[b_last + 1] < r1) ++b_last;
+      if (b_last - b_first + 1 > pmax) pmax = b_last - b_first + 1;
+    }
+    for (int b = 0; b < s.grid; ++b)
+      if (s.tb[b + 1] - s.tb[b] > max_range) max_range = s.tb[b + 1] - s.tb[b];
+  }
+  s.P = pmax;
   // Expected bytes one epilogue thread appends over a piece of T tiles.  A record is a quad of 4 adjacent
   // columns (16 bytes), appended when its maximum beats the row's bound: with a cold bound a whole tile
   // (16 quads) goes out, later about 32/t items per tile t (about 130 items sit above a row's 32-group
@@ -585,6 +645,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.P = s.P;
   sp.CAP = s.CAP;
   sp.nseed = s.nseed;
+  for (int b = 0; b <= s.grid; ++b) sp.tb[b] = s.tb[b];
   sp.mode = env_int("SEAM_DEBUG_SCORE_MODE", 0);   // developer diagnostics only
   sp.cg = cg;
   sp.thr_global = thr;
@@ -601,6 +662,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
     if (sp.mode == 2) score::score_topk_kernel<2><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     else if (sp.mode == 3) score::score_topk_kernel<3><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     else if (sp.mode == 4) score::score_topk_kernel<4><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    else if (sp.mode == 5) score::score_topk_kernel<5><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     else score::score_topk_kernel<0><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     SEAM_LAUNCHED(h, "score_topk_kernel");
   }
