@@ -517,12 +517,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         filter16<VAR, 4, 4>(rb, cgp + 16, gm, wp, cmp, keep, tg);
         ptx::tmem_ld_wait_x16(ra);
         ptx::tmem_ld_x16(taddr + 48, rb);
-        filter16<VAR, 8, 8>(ra, cgp + 32, gm, wp, cmp, keep, tg);
+        // The MMA of the tile after next cannot start before the slowest of the 16 warps has read its
+        // columns, so the last load is waited for right away (half-way through the tile's work, the
+        // scheduler's other warps fill the gap) and the slot handed back before the remaining two chunks.
         ptx::tmem_ld_wait_x16(rb);
-        // this warp's accumulator columns have all been read: hand the TMEM slot back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+        filter16<VAR, 8, 8>(ra, cgp + 32, gm, wp, cmp, keep, tg);
         filter16<VAR, 12, 12>(rb, cgp + 48, gm, wp, cmp, keep, tg);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&cg_empty[acc]);
