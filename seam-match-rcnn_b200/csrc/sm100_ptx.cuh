@@ -49,6 +49,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the
+// time is up, instead of coming back to spin (and to take issue slots from working warps)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Blocking wait with a wall-clock watchdog: a protocol bug traps (the launch fails with an
 // error the host reports) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -59,7 +74,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     // (which itself suspends the warp for a while), a counter and the branch
 #pragma unroll 1
     for (int spins = 0; spins < 4096; ++spins)
-      if (mbar_try_wait(bar, parity)) return;
+      if (mbar_try_wait_hint(bar, parity, 20000u)) return;
     const uint64_t now = globaltimer_ns();
     if (t0 == 0) t0 = now;
     else if (now - t0 > 4000000000ull) __trap();
