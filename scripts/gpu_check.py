@@ -74,7 +74,10 @@ def stage_cand(e):
         nl = P * 4
         off = plan["off_rowbuf"]
         off += (-(ws.data_ptr() + off)) % (CAP * 8)       # the library aligns the base to the sub-list size
-        buf = ws[off:off + Q * nl * CAP * 8].view(torch.int32).view(Q, nl, CAP, 2).cpu()
+        # a record is a quad {w0,w1,w2,w3}: w0 & 63 = quad position in the sub-list's 64-column quarter,
+        # (w1 & 63) | (w2 & 63) << 6 | (w3 & 63) << 12 = gallery tile (256 rows); quarter = sub-list index % 4
+        capq = CAP // 2
+        buf = ws[off:off + Q * nl * CAP * 8].view(torch.int32).view(Q, nl, capq, 4).cpu()
         cnts = ws[plan["off_rowcnt"]:plan["off_rowcnt"] + Q * nl * 4].view(torch.int32).view(Q, nl).cpu()
         ref = approx_margin_ref(q, g)
         top = ref.topk(min(32, G), dim=1).indices
@@ -84,10 +87,16 @@ def stage_cand(e):
             vals, idx = [], []
             for l in range(nl):
                 n = int(cnts[i, l])
-                over += n > CAP
-                n = min(n, CAP)
-                vals.append(buf[i, l, :n, 0].contiguous().view(torch.float32))
-                idx.append(buf[i, l, :n, 1].long())
+                over += n > capq
+                n = min(n, capq)
+                rec = buf[i, l, :n].long()
+                tile = (rec[:, 1] & 63) | ((rec[:, 2] & 63) << 6) | ((rec[:, 3] & 63) << 12)
+                col0 = tile * 256 + (l % 4) * 64 + (rec[:, 0] & 63) * 4
+                cols = col0[:, None] + torch.arange(4)[None, :]
+                v = buf[i, l, :n].contiguous().view(torch.float32)
+                keep = cols < G                                    # padded columns hold NaN
+                vals.append(v[keep])
+                idx.append(cols[keep])
             vals, idx = torch.cat(vals), torch.cat(idx)
             if idx.numel():
                 verr = max(verr, float((vals.double() - ref[i, idx]).abs().max()))
@@ -96,7 +105,7 @@ def stage_cand(e):
                 over += 1000000                            # duplicates would break the top-32 selection
             miss += sum(1 for j in top[i].tolist() if j not in sset)
         print(f"[cand] Q={Q} G={G} plan={ {k: plan[k] for k in ('query_tiles', 'gallery_tiles', 'ctas', 'ctas_per_query_tile', 'list_capacity')} } "
-              f"|cand_v - ref|max={verr:.3e} missing_from_top32={miss} list_len mean={cnt.float().mean():.1f} "
+              f"|cand_v - ref|max={verr:.3e} missing_from_top32={miss} quads per row mean={cnt.float().mean():.1f} "
               f"max={int(cnt.max())} overflow_rows={over} fallback_rows={int(st[0])}")
 
 
