@@ -7,19 +7,17 @@ namespace seam {
 namespace wsort {
 
 // ---- plain float key + 32-bit payload ------------------------------------------------
+// One compare-exchange = 2 shuffles, one min/max whose direction is a predicate (FMNMX), one compare
+// and one select for the payload.  Equal keys keep their own payloads on both sides (no duplicates);
+// keys are never NaN here.
 template <bool DESC>
 __device__ __forceinline__ void cmpx(float& v, uint32_t& p, int lane, int j, int k) {
   const float ov = __shfl_xor_sync(ptx::FULL_MASK, v, j);
   const uint32_t op = __shfl_xor_sync(ptx::FULL_MASK, p, j);
-  const bool up = (lane & k) == 0;
-  const bool lower = (lane & j) == 0;
-  bool keep_min = (lower == up);
-  if (DESC) keep_min = !keep_min;
-  const bool take = keep_min ? (ov < v) : (ov > v);
-  if (take) {
-    v = ov;
-    p = op;
-  }
+  const bool keep_min = ((((lane & k) == 0) == ((lane & j) == 0)) != DESC);
+  const float nv = keep_min ? fminf(v, ov) : fmaxf(v, ov);
+  if (nv != v) p = op;
+  v = nv;
 }
 template <bool DESC>
 __device__ __forceinline__ void sort32(float& v, uint32_t& p, int lane) {
@@ -67,11 +65,26 @@ __device__ __forceinline__ void cmpx_rank2(float& d, int& i, int lane, int j, in
     i = oi;
   }
 }
+// The ranking order as one 64-bit key: order-preserving image of d in the high word, ~i in the low
+// word (lower index = larger key); "ranks before" = larger key.  Keys are unique except for padding
+// entries (d = -inf, i = INT_MAX), for which taking the partner's identical key is harmless.
 __device__ __forceinline__ void sort32_rank2(float& d, int& i, int lane) {
+  uint32_t hi = ptx::float_to_ordered(d), lo = ~(uint32_t)i;
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1)
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) cmpx_rank2(d, i, lane, j, k);
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint32_t ohi = __shfl_xor_sync(ptx::FULL_MASK, hi, j);
+      const uint32_t olo = __shfl_xor_sync(ptx::FULL_MASK, lo, j);
+      const bool keep_better = ((lane & k) == 0) == ((lane & j) == 0);
+      const bool other_better = ohi > hi || (ohi == hi && olo > lo);
+      if (other_better == keep_better) {
+        hi = ohi;
+        lo = olo;
+      }
+    }
+  d = ptx::ordered_to_float(hi);
+  i = (int)~lo;
 }
 // best first
 __device__ __forceinline__ void sort32_rank(float& d, int& i, float& s, int lane) {
