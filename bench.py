@@ -208,7 +208,6 @@ def run_ours(args):
     gen_g = torch.Generator(device="cpu").manual_seed(1000 + rank)
     gal_h = torch.randn(Gs, 256, generator=gen_g).pin_memory()
     out_h = [torch.empty(Q, k).pin_memory(), torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int32).pin_memory()]
-    h2d = seq_h.numel() * 4 + mask_h.numel() + gal_h.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in out_h)
 
     seq_d, mask_d, gal_d = seq_h.to(dev), mask_h.to(dev), gal_h.to(dev)
@@ -299,45 +298,29 @@ def run_ours(args):
     def eager_step():
         return hot_path(seq_d, mask_d, gallery)
 
-    # End to end from pinned host memory: the tracks arrive in NCHUNK host buffers; chunk i+1 is in
-    # flight over PCIe (copy stream) while chunk i is aggregated and -- on one GPU -- scored and its
-    # results copied back, so that only the last chunk's compute is exposed after the last byte lands.
+    # End to end from pinned host memory through the package's host-facing entry points
+    # (retrieval.search_host / HostTrackStream): the tracks cross PCIe in NCHUNK slices on a copy stream;
+    # slice i+1 is in flight while slice i is aggregated and -- on one GPU -- scored and its results
+    # copied back, so that only the last slice's compute is exposed after the last byte lands.  Row 0 of
+    # x3_1_seq (the layout's dummy frame) is not copied.
     NCHUNK = 4
-    cb = [pkg.shard_bounds(per, NCHUNK, c) for c in range(NCHUNK)]
-    seq_hc = [seq_h[:, a:b].contiguous().pin_memory() for a, b in cb]
-    mask_hc = [mask_h[a:b].contiguous().pin_memory() for a, b in cb]
-    copy_stream = torch.cuda.Stream(device=dev)
+    track_stream = pkg.HostTrackStream(eng, NCHUNK)
+    h2d = track_stream.h2d_bytes(seq_h, mask_h) + gal_h.numel() * 4
 
     def e2e_step():
+        if world == 1:
+            pkg.search_host(eng, seq_h, mask_h, gal_h, k, out=out_h, stream=track_stream, index_offset=rank * Gs)
+            return
         main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)
-        staged = []
-        with torch.cuda.stream(copy_stream):
+        track_stream.copy_stream.wait_stream(main)
+        with torch.cuda.stream(track_stream.copy_stream):
             g_d = gal_h.to(dev, non_blocking=True)
             ev_g = torch.cuda.Event()
-            ev_g.record(copy_stream)
-            for c in range(NCHUNK):
-                s_c = seq_hc[c].to(dev, non_blocking=True)
-                m_c = mask_hc[c].to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                staged.append((s_c, m_c, ev))
+            ev_g.record(track_stream.copy_stream)
         main.wait_event(ev_g)
         g = eng.prepare_gallery(g_d, index_offset=rank * Gs)
         g_d.record_stream(main)
-        parts = []
-        for c, (s_c, m_c, ev) in enumerate(staged):
-            main.wait_event(ev)
-            s_c.record_stream(main)
-            m_c.record_stream(main)
-            q_c = eng.aggregate(s_c, m_c)
-            if world == 1:
-                a, b = cb[c]
-                res = eng.score_topk(q_c, g, k)
-                for dst, src in zip(out_h, res):
-                    dst[a:b].copy_(src, non_blocking=True)
-            else:
-                parts.append(q_c)
+        parts = [q_c for _, _, q_c in track_stream.chunks(seq_h, mask_h)]
         if world > 1:
             q = torch.cat(parts, 0)
             if even:

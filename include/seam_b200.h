@@ -163,6 +163,14 @@ int seam_rank_of_target(seam_handle* h, const float* q, int Q, const float* g, i
 int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, const int32_t* idx, int N, int Q,
                     int k, float* out_score, float* out_margin, int32_t* out_idx, void* stream);
 
+/* Host -> device upload of a slice of tracks, tracks [lo, hi) of a HOST x3_1_seq (1+Tmax, Q, 256) fp32
+ * (the reference keeps every feature in host memory between the detector and the scorer,
+ * evaluate_movingfashion.py:45-92, 253): one pitched asynchronous copy of the frame rows 1..Tmax into
+ * the device tensor seq_dev (1+Tmax, hi-lo, 256); row 0 (the layout's dummy frame,
+ * models/match_head.py:101-111) is neither read nor written.  Pinned host memory makes it asynchronous. */
+int seam_upload_tracks(seam_handle* h, const float* seq_host, int Tmax, int Q, int lo, int hi, float* seq_dev,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,6 +99,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_score_dense.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     lib.seam_rank_of_target.restype = i32
     lib.seam_rank_of_target.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    lib.seam_upload_tracks.restype = i32
+    lib.seam_upload_tracks.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.seam_merge_topk.restype = i32
     lib.seam_merge_topk.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
 

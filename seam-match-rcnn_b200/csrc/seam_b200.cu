@@ -748,6 +748,20 @@ int seam_rank_of_target(seam_handle* h, const float* q, int Q, const float* g, i
   return SEAM_OK;
 }
 
+int seam_upload_tracks(seam_handle* h, const float* seq_host, int Tmax, int Q, int lo, int hi, float* seq_dev,
+                       void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (Tmax < 0 || Q < 0 || lo < 0 || hi < lo || hi > Q) return fail(h, SEAM_ERR_BAD_ARG, "seam_upload_tracks: bad range");
+  if (Tmax == 0 || hi == lo) return SEAM_OK;
+  if (!seq_host || !seq_dev) return fail(h, SEAM_ERR_BAD_ARG, "seam_upload_tracks: null pointer");
+  DeviceGuard guard(h->device);
+  const size_t n = (size_t)(hi - lo);
+  SEAM_CUDA(h, cudaMemcpy2DAsync(seq_dev + n * 256, n * 1024, seq_host + ((size_t)Q + (size_t)lo) * 256,
+                                 (size_t)Q * 1024, n * 1024, (size_t)Tmax, cudaMemcpyHostToDevice,
+                                 static_cast<cudaStream_t>(stream_)));
+  return SEAM_OK;
+}
+
 int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, const int32_t* idx, int N, int Q,
                     int k, float* out_score, float* out_margin, int32_t* out_idx, void* stream_) {
   if (!h) return SEAM_ERR_BAD_ARG;

@@ -253,6 +253,19 @@ class SeamEngine:
                                                   self._stream()))
         return rank, margin
 
+    def upload_tracks(self, seq_host: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+        """Tracks [lo, hi) of a HOST ``x3_1_seq (1+Tmax, Q, 256)`` -> device ``(1+Tmax, hi-lo, 256)`` on the
+        current stream with one pitched copy of the frame rows (row 0, the dummy frame, stays untouched)."""
+        if seq_host.device.type != "cpu" or seq_host.dtype != torch.float32 or not seq_host.is_contiguous():
+            raise SeamError(2, "upload_tracks: seq_host must be a contiguous fp32 host tensor")
+        T1, Q, D = seq_host.shape
+        if D != D_MODEL:
+            raise SeamError(3, f"upload_tracks: feature size {D} != {D_MODEL}")
+        out = torch.empty((T1, hi - lo, D), dtype=torch.float32, device=self.device)
+        self._check(self._lib.seam_upload_tracks(self._h, seq_host.data_ptr(), T1 - 1, Q, lo, hi, out.data_ptr(),
+                                                 self._stream()))
+        return out
+
     def merge_topk(self, scores: torch.Tensor, margins: torch.Tensor, idx: torch.Tensor):
         """Merge (N,Q,k) per-shard lists into (Q,k)."""
         N, Q, k = scores.shape

@@ -58,6 +58,80 @@ def search(engine: SeamEngine, seq: torch.Tensor, mask: Optional[torch.Tensor], 
 
 
 # ----------------------------------------------------------------------------------------
+# from HOST memory (the reference's eval keeps every feature in host memory between the detector
+# and the scorer, evaluate_movingfashion.py:45-92, and moves one product's frames to the device per
+# query, :253-262)
+# ----------------------------------------------------------------------------------------
+class HostTrackStream:
+    """Streams a host ``x3_1_seq (1+Tmax, Q, 256)`` / ``x3_1_mask (Q, 1+Tmax)`` pair to the device in
+    ``nchunk`` slices of tracks on a private copy stream and aggregates each slice as soon as it has
+    landed, so that the PCIe transfer of slice i+1 overlaps the kernels of slice i.  Only the frame rows
+    1..Tmax cross the bus: row 0 is the layout's dummy (models/match_head.py:101-111) and is never read.
+    Pinned host tensors make the copies asynchronous; pageable ones work but serialise."""
+
+    def __init__(self, engine: SeamEngine, nchunk: int = 4):
+        self.engine = engine
+        self.nchunk = int(nchunk)
+        self.copy_stream = torch.cuda.Stream(device=engine.device)
+
+    def h2d_bytes(self, seq_h: torch.Tensor, mask_h: Optional[torch.Tensor]) -> int:
+        n = (seq_h.shape[0] - 1) * seq_h.shape[1] * seq_h.shape[2] * seq_h.element_size()
+        return n + (mask_h.numel() * mask_h.element_size() if mask_h is not None else 0)
+
+    def chunks(self, seq_h: torch.Tensor, mask_h: Optional[torch.Tensor]):
+        """Yields (lo, hi, descriptors (hi-lo,256) on the device) per slice, in order, on the current stream."""
+        eng, dev = self.engine, self.engine.device
+        T1, Q = seq_h.shape[0], seq_h.shape[1]
+        main = torch.cuda.current_stream(dev)
+        self.copy_stream.wait_stream(main)
+        staged = []
+        with torch.cuda.stream(self.copy_stream):
+            for c in range(self.nchunk):
+                lo, hi = shard_bounds(Q, self.nchunk, c)
+                if hi == lo:
+                    continue
+                s_d = eng.upload_tracks(seq_h, lo, hi)               # one pitched copy of rows 1..Tmax
+                m_d = mask_h[lo:hi].to(dev, non_blocking=True) if mask_h is not None else None
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                staged.append((lo, hi, s_d, m_d, ev))
+        for lo, hi, s_d, m_d, ev in staged:
+            main.wait_event(ev)
+            s_d.record_stream(main)
+            if m_d is not None:
+                m_d.record_stream(main)
+            yield lo, hi, eng.aggregate(s_d, m_d)
+
+
+def search_host(engine: SeamEngine, seq_h: torch.Tensor, mask_h: Optional[torch.Tensor], gallery_h: torch.Tensor,
+                k: int = 20, out: Optional[Sequence[torch.Tensor]] = None, stream: Optional[HostTrackStream] = None,
+                index_offset: int = 0):
+    """Host tensors in, host tensors out: gallery upload + preparation, chunked track upload overlapped
+    with aggregation and scoring, results copied back per chunk into ``out`` (three (Q,k) host tensors:
+    scores fp32, margins fp32, idx int32; allocated pinned when not given).  Returns ``out``; the caller
+    synchronises the current stream before reading it."""
+    dev = engine.device
+    stream = stream or HostTrackStream(engine)
+    Q = seq_h.shape[1]
+    if out is None:
+        out = [torch.empty((Q, k), dtype=dt).pin_memory() for dt in (torch.float32, torch.float32, torch.int32)]
+    main = torch.cuda.current_stream(dev)
+    stream.copy_stream.wait_stream(main)
+    with torch.cuda.stream(stream.copy_stream):
+        g_d = gallery_h.to(dev, non_blocking=True)
+        ev_g = torch.cuda.Event()
+        ev_g.record(stream.copy_stream)
+    main.wait_event(ev_g)
+    g_d.record_stream(main)
+    gallery = engine.prepare_gallery(g_d, index_offset=index_offset)
+    for lo, hi, q_c in stream.chunks(seq_h, mask_h):
+        res = engine.score_topk(q_c, gallery, k)
+        for dst, src in zip(out, res):
+            dst[lo:hi].copy_(src, non_blocking=True)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # gallery-sharded multi-GPU search
 # ----------------------------------------------------------------------------------------
 class ShardedRetriever:

@@ -143,3 +143,26 @@ def test_evaluate_aggregated_report(model, weights):
     ranks = so.rank_of_target(x5, target)
     assert torch.equal(rep.ranks.cpu().long(), ranks)
     assert rep.hits == [int((ranks < k).sum()) for k in (1, 5, 10, 20)]
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_search_from_host_memory(model, weights, pinned):
+    """retrieval.search_host: host tensors in, host tensors out, tracks streamed in slices (row 0 of
+    x3_1_seq, the dummy frame, filled with NaN: it must never be read or copied); same results as
+    the device-resident search and as the oracle."""
+    Q, T, G, k = 203, 7, 777, 20
+    seq, mask, _ = so.synth_tracks(Q, T, seed=11, ragged=(1, 7))
+    seq[0] = float("nan")
+    qref, _ = so.aggregate_tracks(seq, mask, weights)
+    gal = so.synth_gallery(G, 11, qref)
+    eng = model._engine_for(torch.device(DEV))
+    model._sync_weights(eng)
+    hs, hm, hg = (t.pin_memory() if pinned else t for t in (seq, mask, gal))
+    out = pkg.search_host(eng, hs, hm, hg, k, stream=pkg.HostTrackStream(eng, nchunk=3))
+    torch.cuda.synchronize()
+    s_d, m_d, i_d = pkg.search(eng, seq.to(DEV), mask.to(DEV), gal.to(DEV), k)
+    assert torch.equal(out[2], i_d.cpu())
+    assert torch.equal(out[1], m_d.cpu()) and torch.equal(out[0], s_d.cpu())
+    s_ref, d_ref, i_ref = so.rank_topk(so.pair_logits(qref, gal, weights), k)
+    assert torch.equal(out[2].long(), i_ref)
+    assert (out[1] - d_ref).abs().max() <= TOL_LOGIT
