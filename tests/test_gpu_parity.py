@@ -154,6 +154,25 @@ def test_topk_near_duplicates_take_exhaustive_path(weights, engine):
     assert_topk_matches(ix, mg, sc, so.logit_margin(x5), so.match_scores(x5), 20)
 
 
+def test_topk_rising_gallery_overflows_candidate_lists(weights, engine):
+    """A gallery whose margins rise with the row index makes nearly every new item beat the running
+    bound: the per-thread candidate lists fill up, close, and the affected rows must be flagged and
+    re-ranked exhaustively -- never silently truncated."""
+    dw = (weights["last.weight"][1] - weights["last.weight"][0]).float()
+    c = int(dw.argmax())
+    assert dw[c] > 0
+    rs = np.random.RandomState(8)
+    Q, G, k = 96, 40000, 20
+    q = torch.from_numpy(rs.randn(Q, 256).astype(np.float32))
+    g = 0.05 * torch.from_numpy(rs.randn(G, 256).astype(np.float32))
+    g[:, c] += torch.linspace(0.0, 40.0, G)              # dw . g^2 grows with the row index
+    x5 = so.pair_logits(q, g, weights)
+    gal = engine.prepare_gallery(g.to(DEV))
+    sc, mg, ix, stats = engine.score_topk(q.to(DEV), gal, k, return_stats=True)
+    assert int(stats[0]) > 0, "expected rows whose lists overflowed"
+    assert_topk_matches(ix, mg, sc, so.logit_margin(x5), so.match_scores(x5), k, tol=2e-3)
+
+
 def test_topk_fp16_overflow_is_safe(weights, engine):
     """Values beyond the fp16 range cannot go through the tensor-core pass; they are flagged and
     the exhaustive fp32 path answers."""
