@@ -106,19 +106,24 @@ struct Segment {
     return i < n_seed ? nt0 + (int)((unsigned)((2 * i + 1) * n_main) / (unsigned)(2 * n_seed)) : nt0 + (i - n_seed);
   }
 };
-// A segment that begins within the CTA's first WARM_TILES tiles previews min(nseed, n_main) sample
-// tiles: the whole grid starts cold at the same moment.  Later segments start from the bound the
-// other CTAs sweeping the same rows have published in thr_global (every 8 tiles) instead.
-constexpr int WARM_TILES = 16;
-__device__ __forceinline__ Segment segment_at(const Params& p, long long t_begin, long long t, long long t_end,
-                                              long long& next) {
+// Sweep order and sampling.  The whole grid starts cold at the same moment, so a row's bound has to be
+// warmed by somebody: the segment that contains the row's first gallery tile (its "head") previews
+// min(nseed, n_main) sample tiles, and so does whatever segment a CTA sweeps first.  A CTA sweeps the
+// segments of its range LAST FIRST: the last one is normally a head, the first one the tail of a row
+// whose head is the first thing the previous CTA sweeps -- by the time this CTA gets to the tail the
+// row's bound has long been published in thr_global (after the sample sweep, then every 8 tiles), and
+// the tail starts warm without samples.  Every row is thus sampled once, not once per piece.
+__device__ __forceinline__ Segment segment_before(const Params& p, long long t_begin, long long t_hi, long long t_end,
+                                                  long long& next_hi) {
   Segment s;
-  s.m = (int)(t / p.ntiles_n);
-  s.nt0 = (int)(t - (long long)s.m * p.ntiles_n);
-  next = min(t_end, (long long)(s.m + 1) * p.ntiles_n);
-  s.n_main = (int)(next - t);
-  s.n_seed = (t - t_begin < WARM_TILES) ? min(p.nseed, s.n_main) : 0;
+  s.m = (int)((t_hi - 1) / p.ntiles_n);
+  const long long row0 = (long long)s.m * p.ntiles_n;
+  const long long start = max(t_begin, row0);
+  s.nt0 = (int)(start - row0);
+  s.n_main = (int)(t_hi - start);
+  s.n_seed = (t_hi == t_end || start == row0) ? min(p.nseed, s.n_main) : 0;
   s.ntiles_n = p.ntiles_n;
+  next_hi = start;
   return s;
 }
 
@@ -343,9 +348,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ================================================================= TMA producer
     if (lane == 0) {
       uint32_t stage = 0, sphase = 0, iphase = 0;
-      long long t = t_begin, next;
-      while (t < t_end) {
-        const Segment sg = segment_at(p, t_begin, t, t_end, next);
+      long long t = t_end, next;
+      while (t > t_begin) {
+        const Segment sg = segment_before(p, t_begin, t, t_end, next);
         ptx::mbar_wait(a_empty, iphase ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, NKB * A_KB_BYTES);
         for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, sg.m * BM);
@@ -372,9 +377,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t idesc = ptx::umma_idesc(0 /*fp16*/, BM, BN);
       const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
       uint32_t stage = 0, sphase = 0, iphase = 0, acc = 0, aphase = 0;
-      long long t = t_begin, next;
-      while (t < t_end) {
-        const Segment sg = segment_at(p, t_begin, t, t_end, next);
+      long long t = t_end, next;
+      while (t > t_begin) {
+        const Segment sg = segment_before(p, t_begin, t, t_end, next);
         const int n = sg.count();
         ptx::mbar_wait(a_full, iphase);
         for (int i = 0; i < n; ++i) {
@@ -413,9 +418,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // {gallery tile | -1 = done, flags, query tile, piece} for the epilogue warps, which therefore
     // carry no segment bookkeeping of their own.
     uint32_t acc = 0, aphase = 0;
-    long long t = t_begin, next;
-    while (t < t_end) {
-      const Segment sg = segment_at(p, t_begin, t, t_end, next);
+    long long t = t_end, next;
+    while (t > t_begin) {
+      const Segment sg = segment_before(p, t_begin, t, t_end, next);
       const int n = sg.count();
       const int piece = blockIdx.x - cta_of_tile(p, gridDim.x, (long long)sg.m * p.ntiles_n);
       for (int i = 0; i < n; ++i) {
@@ -540,7 +545,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float4 o = *reinterpret_cast<const float4*>(thr_x + R * NQ);
           thr = fmaxf(thr, fminf(fminf(o.x, o.y), fminf(o.z, o.w)));
         }
-        if ((itile & 7) == 7 && (st & ST_ROW)) {   // exchange with the other CTAs sweeping these rows
+        if (((itile & 7) == 7 || seed_end) && (st & ST_ROW)) {   // exchange with the other CTAs sweeping these rows
           const uint32_t old = atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
           thr = fmaxf(thr, ptx::ordered_to_float(old));
         }

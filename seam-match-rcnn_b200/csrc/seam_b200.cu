@@ -447,9 +447,9 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
   if (s.grid > score::MAX_GRID) s.grid = score::MAX_GRID;
   s.nseed = env_int("SEAM_SCORE_NSEED", 4);
   // Cost-balanced contiguous ranges.  A tile costs 1; a segment start costs SEG_COST (query tile load,
-  // epilogue hand-over) plus, when it lies within the CTA's first WARM_TILES tiles (score_tc.cuh), its
-  // min(nseed, length) threshold-only sample tiles.  walk() cuts ranges of cost <= target; the smallest
-  // target whose last range also fits is found by bisection.
+  // epilogue hand-over); a segment that holds its row's first gallery tile -- or is all a CTA has --
+  // also sweeps min(nseed, length) threshold-only sample tiles (score_tc.cuh, segment_before).  walk()
+  // cuts ranges of cost <= target; the smallest target whose last range also fits is found by bisection.
   const double SEG_COST = 0.35;
   const long long ntn = s.ntiles_n, total = s.total_tiles;
   auto walk = [&](double target, int* tb) -> double {   // returns the cost of the last CTA's range
@@ -462,9 +462,11 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
       while (pos < total) {
         const long long row_end = (pos / ntn + 1) * ntn;
         const long long seg_len = row_end - pos;
-        const bool cold = pos - t0 < score::WARM_TILES;
-        // sample tiles if the whole rest of the row were taken; a shorter cut samples at most as many
-        const double over = SEG_COST + (cold ? (double)(seg_len < s.nseed ? seg_len : s.nseed) : 0.0);
+        const bool head = pos % ntn == 0;
+        const double samples = (double)(seg_len < s.nseed ? seg_len : s.nseed);
+        double over = SEG_COST + (head ? samples : 0.0);
+        // the tail of a row that leaves no room for the next row's head is all this CTA sweeps: sampled
+        if (!head && pos == t0 && (double)seg_len + over + SEG_COST + s.nseed + 1.0 > target) over += samples;
         long long n = seg_len;
         if (!last) {
           const double room = target - cost - over;
