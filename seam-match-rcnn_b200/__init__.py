@@ -11,12 +11,13 @@ from ._lib import SeamError, declared_symbols, load as load_library          # n
 from ._build import build as build_library, LIB_PATH                          # noqa: F401
 from .engine import SeamEngine, PreparedGallery, get_engine                   # noqa: F401
 from .modules import NONLocalBlock1D, MatchPredictor, TemporalAggregationNLB  # noqa: F401
-from .retrieval import (ShardedRetriever, RetrievalReport, evaluate_aggregated, search,   # noqa: F401
+from .retrieval import (ShardedRetriever, RetrievalReport, ProductReport, evaluate_aggregated,   # noqa: F401
+                        evaluate_products, search,
                         search_host, HostTrackStream, shard_bounds, all_gather_rows, K_THRESHOLDS)
 
 __all__ = [
     "SeamError", "SeamEngine", "PreparedGallery", "get_engine", "NONLocalBlock1D", "MatchPredictor",
     "TemporalAggregationNLB", "ShardedRetriever", "RetrievalReport", "evaluate_aggregated", "search",
-    "search_host", "HostTrackStream",
+    "search_host", "HostTrackStream", "ProductReport", "evaluate_products",
     "shard_bounds", "all_gather_rows", "build_library", "load_library", "declared_symbols", "K_THRESHOLDS",
 ]

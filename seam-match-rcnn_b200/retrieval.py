@@ -211,3 +211,73 @@ def evaluate_aggregated(engine: SeamEngine, seq, mask, gallery: torch.Tensor, ta
     hits = [int((r < k).sum()) for k in k_thresholds]
     n = max(1, q.shape[0])
     return RetrievalReport(ranks=ranks, hits=hits, accuracies=[h / n for h in hits], topk_scores=sc, topk_idx=ix)
+
+
+@dataclass
+class ProductReport:
+    """The four accuracy rows the eval script writes to its CSV (evaluate_movingfashion.py:435-443, in per
+    cent) and its return values (:340, :351, :356), plus the per-frame rank statistics (:425-429)."""
+    perf: torch.Tensor                  # (4, len(k_thresholds)) float32, per cent: per frame / best frame of the
+                                        # product / average descriptor / aggregated descriptor
+    ret: Tuple[float, float, float]     # (ret1, ret2, ret3) = top-1 of rows 0, 2, 3 as fractions
+    frame_ranks: torch.Tensor           # (N,) int32
+    product_ranks: torch.Tensor         # (3, P) int32: best frame, average descriptor, aggregated descriptor
+    rank_median: float
+    rank_q1: float
+    rank_q3: float
+
+
+def evaluate_products(engine: SeamEngine, frame_desc: torch.Tensor, frame_product: torch.Tensor,
+                      shop_desc: torch.Tensor, target: torch.Tensor, frame_last: Tuple[torch.Tensor, torch.Tensor],
+                      seq: torch.Tensor, mask: Optional[torch.Tensor], shop_aggr: torch.Tensor,
+                      aggr_last: Tuple[torch.Tensor, torch.Tensor],
+                      k_thresholds: Sequence[int] = K_THRESHOLDS) -> ProductReport:
+    """The per-product loop of the eval script (evaluate_movingfashion.py:157-330) for all products at once,
+    for the variants that rank with a single descriptor per query:
+
+    row 0  every tracked frame box on its own: ``compute_ranking`` (:95-100) with ``match_predictor.last``
+           (``frame_last`` = the ``w, b`` the detector emits, models/video_matchrcnn.py:297-314), hits :223-232;
+    row 1  the product's best frame ("Product Max", :233-241): minimum of its frames' ranks;
+    row 2  the average of the product's frame descriptors (:279-292), same scorer;
+    row 3  the aggregated descriptor (:252-277) with ``temporal_aggregator.last`` (``aggr_last``).
+
+    ``frame_desc (N,256)`` are the match features of the tracked boxes, ``frame_product (N,)`` the product
+    (0..P-1) each belongs to, ``shop_desc (G,256)`` / ``shop_aggr (G,256)`` the shop boxes' match features
+    and aggregator descriptors, ``target (P,)`` each product's shop row; ``seq`` / ``mask`` the aggregator
+    input of the P tracks.  Ranks come from the fp32 direct-form kernel (``seam_rank_of_target``), i.e. the
+    position the reference reads out of its full argsort, without sorting.  The reference runs rows 0-2 in
+    numpy fp16 (:82-100); these are the fp32 values of the same formulas.
+    The average / maximum *distance* fusions (:294-316) reduce a (frames x gallery) score matrix per product
+    and are not covered here."""
+    dev = engine.device
+    frame_desc = frame_desc.to(dev, torch.float32)
+    fp = frame_product.to(dev, torch.int64)
+    target = target.to(dev, torch.int64)
+    P = int(target.shape[0])
+    shop_desc = shop_desc.to(dev, torch.float32).contiguous()
+    ks = list(k_thresholds)
+
+    engine.load_scorer(*frame_last)
+    fr, _ = engine.rank_of_target(frame_desc, shop_desc, target[fp])
+    big = torch.iinfo(torch.int32).max
+    best = torch.full((P,), big, dtype=torch.int32, device=dev).scatter_reduce(0, fp, fr, "amin")
+    cnt = torch.zeros((P,), dtype=torch.float32, device=dev).index_add_(0, fp, torch.ones_like(fr, dtype=torch.float32))
+    avg = torch.zeros((P, frame_desc.shape[1]), dtype=torch.float32, device=dev).index_add_(0, fp, frame_desc)
+    has = cnt > 0
+    avg = avg / cnt.clamp(min=1.0)[:, None]
+    ar, _ = engine.rank_of_target(avg, shop_desc, target)
+    ar = torch.where(has, ar, torch.full_like(ar, big))
+
+    engine.load_scorer(*aggr_last)
+    rep = evaluate_aggregated(engine, seq, mask, shop_aggr, target, ks)
+
+    def row(r, n):
+        return [float((r < k).sum()) / max(1, n) for k in ks]
+
+    n_frames = int(fr.shape[0])
+    perf = torch.tensor([row(fr, n_frames), row(best, P), row(ar, P), row(rep.ranks, P)], dtype=torch.float32) * 100.0
+    frf = fr.float()
+    qs = torch.quantile(frf, torch.tensor([0.25, 0.5, 0.75], device=dev)) if n_frames else torch.zeros(3)
+    return ProductReport(perf=perf, ret=(perf[0, 0].item() / 100.0, perf[2, 0].item() / 100.0, perf[3, 0].item() / 100.0),
+                         frame_ranks=fr, product_ranks=torch.stack([best, ar, rep.ranks.to(torch.int32)]),
+                         rank_median=float(qs[1]), rank_q1=float(qs[0]), rank_q3=float(qs[2]))

@@ -166,3 +166,46 @@ def test_search_from_host_memory(model, weights, pinned):
     s_ref, d_ref, i_ref = so.rank_topk(so.pair_logits(qref, gal, weights), k)
     assert torch.equal(out[2].long(), i_ref)
     assert (out[1] - d_ref).abs().max() <= TOL_LOGIT
+
+
+def test_evaluate_products_rows(model, weights):
+    """evaluate_movingfashion.py:157-330 for all products at once: per-frame, best-frame, average-descriptor
+    and aggregated-descriptor ranks / accuracy rows against the same formulas in torch fp32."""
+    P, T, G = 31, 6, 140
+    seq, mask, lens = so.synth_tracks(P, T, seed=4, ragged=(1, 6))
+    lens = [int(x) for x in lens]
+    rs = np.random.RandomState(4)
+    frame_product = torch.tensor([p for p in range(P) for _ in range(lens[p])])
+    frame_desc = torch.from_numpy(rs.randn(len(frame_product), 256).astype(np.float32))
+    shop_desc = torch.from_numpy(rs.randn(G, 256).astype(np.float32))
+    target = torch.from_numpy(rs.permutation(G)[:P].astype(np.int64))
+    shop_desc[target[frame_product[::3]]] = frame_desc[::3] + 0.3 * torch.from_numpy(
+        rs.randn(len(frame_desc[::3]), 256).astype(np.float32))          # some frames resemble their product
+    qref, _ = so.aggregate_tracks(seq, mask, weights)
+    shop_aggr = so.synth_gallery(G, 4, None)
+    shop_aggr[target] = qref + 0.2 * torch.from_numpy(rs.randn(P, 256).astype(np.float32))
+    fw = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2, 256)).astype(np.float32))
+    fb = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2,)).astype(np.float32))
+    aw, ab = weights["last.weight"], weights["last.bias"]
+
+    eng = model._engine_for(torch.device(DEV))
+    model._sync_weights(eng)
+    rep = pkg.evaluate_products(eng, frame_desc, frame_product, shop_desc, target, (fw, fb),
+                                seq.to(DEV), mask.to(DEV), shop_aggr, (aw, ab))
+
+    wf = dict(weights)
+    wf["last.weight"], wf["last.bias"] = fw, fb
+    fr = so.rank_of_target(so.pair_logits(frame_desc, shop_desc, wf), target[frame_product])
+    best = torch.stack([fr[frame_product == p].min() for p in range(P)])
+    avg = torch.stack([frame_desc[frame_product == p].mean(0) for p in range(P)])
+    ar = so.rank_of_target(so.pair_logits(avg, shop_desc, wf), target)
+    gr = so.rank_of_target(so.pair_logits(qref, shop_aggr, weights), target)
+    assert torch.equal(rep.frame_ranks.cpu().long(), fr)
+    assert torch.equal(rep.product_ranks.cpu().long(), torch.stack([best, ar, gr]))
+    ks = (1, 5, 10, 20)
+    want = torch.tensor([[float((r < k).sum()) / n * 100 for k in ks]
+                         for r, n in ((fr, len(fr)), (best, P), (ar, P), (gr, P))])
+    assert torch.allclose(rep.perf, want, atol=1e-4)
+    assert abs(rep.ret[2] - float((gr < 1).sum()) / P) < 1e-6
+    assert rep.rank_median == float(torch.quantile(fr.float(), 0.5))
+    model._sync_weights(eng)                      # leave the shared engine with the module's own scorer
