@@ -146,17 +146,23 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
   const long long stride = (long long)gridDim.x * NW;
   const long long first = (long long)blockIdx.x * NW + warp;
 
-  // start the copies of one track into a slot; returns nothing, the length goes to slot_len
-  auto issue = [&](long long track, int slot) {
+  // A track's length comes from lens[] or from its mask row.  peek() only issues that (dependent, ~1 us)
+  // load -- one track ahead of its use, so that its latency hides behind the current track's arithmetic --
+  // and issue() turns the loaded word into the length and starts the frame copies into a slot.
+  auto peek = [&](long long track) -> int {
+    if (track >= p.Q) return 0;
+    if (p.lens) return p.lens[track];
+    if (p.mask) return lane <= Tmax ? (int)p.mask[(size_t)track * (1 + Tmax) + lane] : 0;
+    return 0;
+  };
+  auto issue = [&](long long track, int slot, int raw) {
     int len = 0;
     if (track < p.Q) {
       if (p.lens) {
-        len = p.lens[track];
+        len = raw;
       } else if (p.mask) {
         // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
-        const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
-        const bool set = lane <= Tmax && m[lane] != 0;
-        const uint32_t b = __ballot_sync(ptx::FULL_MASK, set);
+        const uint32_t b = __ballot_sync(ptx::FULL_MASK, raw != 0);
         const int end = b ? __ffs(b) - 1 : 1 + Tmax;
         len = end - 1;
       } else {
@@ -176,6 +182,14 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
     }
   };
 
+  // SLOTS == 1: the single buffer is re-armed for the next track as soon as the current one's
+  // frames sit in registers, so its copy overlaps the rest of the computation.  The first copies start
+  // before the folded vectors are fetched.
+  constexpr int AHEAD = SLOTS == 1 ? 1 : SLOTS - 1;       // tracks in flight ahead of the one being processed
+#pragma unroll 1
+  for (int i = 0; i < AHEAD; ++i) issue(first + i * stride, i, peek(first + i * stride));
+  int raw_next = peek(first + (long long)AHEAD * stride);  // for the next issue() below
+
   // folded vectors at this lane's two float4 positions
   const float* fold = p.fold;
   const Vec8 ut = load_vec8(fold + Fold::U_THETA, lane);
@@ -188,11 +202,6 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
   const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
                        : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
 
-  // SLOTS == 1: the single buffer is re-armed for the next track as soon as the current one's
-  // frames sit in registers, so its copy overlaps the rest of the computation.
-#pragma unroll 1
-  for (int i = 0; i < (SLOTS == 1 ? 1 : SLOTS - 1); ++i) issue(first + i * stride, i);
-
   int it = 0;
 #pragma unroll 1
   for (long long track = first; track < p.Q; track += stride, ++it) {
@@ -200,7 +209,8 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
     const uint32_t phase = (uint32_t)(it / SLOTS) & 1u;
     if constexpr (SLOTS > 1) {
       __syncwarp();                                  // every lane is done with the slot being refilled
-      issue(track + (long long)(SLOTS - 1) * stride, (it + SLOTS - 1) % SLOTS);
+      issue(track + (long long)(SLOTS - 1) * stride, (it + SLOTS - 1) % SLOTS, raw_next);
+      raw_next = peek(track + (long long)SLOTS * stride);
     }
     ptx::mbar_wait(&bars[slot], phase);
     const int len = slot_len[slot];
@@ -241,7 +251,8 @@ __global__ void __launch_bounds__(Cfg<TR>::NW * 32, 1) aggregate_warp_kernel(con
       }
       if constexpr (SLOTS == 1) {
         __syncwarp();                                // all lanes hold their frames in registers
-        issue(track + stride, 0);
+        issue(track + stride, 0, raw_next);
+        raw_next = peek(track + 2 * stride);
       }
       if constexpr (NV <= 16) {
         const float tot = treduce<16>(acc, lane);
