@@ -140,6 +140,31 @@ def test_topk_vs_oracle(Q, G, k, weights, engine):
     assert_topk_matches(ix, mg, sc, so.logit_margin(x5), so.match_scores(x5), k)
 
 
+def _random_shapes():
+    rs = np.random.RandomState(20261017)
+    shapes = []
+    for _ in range(10):
+        Q = int(rs.choice([1, 2, 37, 127, 128, 129, 300, 640]))
+        G = int(rs.choice([1, 5, 255, 256, 257, 1023, 4097, 12000, 26000]))
+        shapes.append((Q, G, int(rs.randint(1, 33))))
+    return shapes + [(300, 26000, 20), (640, 12000, 32), (2, 26000, 7)]
+
+
+@pytest.mark.parametrize("Q,G,k", _random_shapes())
+def test_topk_random_shapes(Q, G, k, weights, engine):
+    """Tile edges, single-tile and many-piece partitions, every k up to 32: the work decomposition
+    (cost-balanced ranges, sweep order, sample tiles, sub-list slots) must never show in the results."""
+    rs = np.random.RandomState(Q * 100003 + G * 17 + k)
+    q = torch.from_numpy(rs.randn(Q, 256).astype(np.float32))
+    g = so.synth_gallery(G, seed=Q + 3 * G + k, planted=q)
+    x5 = so.pair_logits(q, g, weights, chunk=64)
+    gal = engine.prepare_gallery(g.to(DEV))
+    sc, mg, ix, stats = engine.score_topk(q.to(DEV), gal, k, return_stats=True)
+    assert_topk_matches(ix, mg, sc, so.logit_margin(x5), so.match_scores(x5), k)
+    if k <= 20:   # beyond ~24 the 2*eps window around the k-th value often fills the 32 nominated lanes
+        assert int(stats[0]) <= max(1, Q // 20), "the candidate pass should certify nearly every row"
+
+
 def test_topk_near_duplicates_take_exhaustive_path(weights, engine):
     """A gallery of near-identical items defeats the fp16 candidate pass (gaps below its error
     bound): those rows must be detected and re-ranked exhaustively, still matching the oracle."""
