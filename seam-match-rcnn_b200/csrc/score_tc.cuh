@@ -8,22 +8,23 @@
 // fp32 accumulation in TMEM), + cg_j in the epilogue.  The (Q,G) matrix never leaves the SM.
 //
 // Candidate filter (branch-free).  Every query row keeps a lower bound thr on its 32nd best v:
-// each of the row's 4 epilogue threads deals its columns into 16 disjoint groups and keeps their
-// running maxima (one FMNMX3 per two accumulator elements); at least 8 distinct gallery items
-// sit at or above the 8th largest of a thread's 16 maxima, so the smallest of the four threads'
-// values is such a bound -- with about 60 items above it (a plain minimum over 32 groups would
-// leave 125).  An element is appended to the row's candidate list in global memory iff v > thr
-// (one predicated 8-byte store).  Nothing is ever pruned or re-ordered on the SM; the re-score
-// kernel (score_exact.cuh) selects the best 32 of a row's list and certifies the result.
-// Bounds are shared between the 4 threads of a row through shared memory after every tile and
-// between CTAs working on the same rows through global memory (atomicMax on an
-// order-preserving integer image of the float).  To warm the bound before anything is
-// appended, every segment first sweeps a few sample tiles spread over its range in
-// threshold-only mode.
+// each of the row's 4 epilogue threads keeps 16 running group maxima (a group = 4 adjacent columns
+// of every tile; groups are pairwise disjoint); at least 8 distinct gallery items sit at or above the
+// 8th largest of a thread's 16 maxima, so the smallest of the four threads' values is such a bound --
+// with about 60 items above it.  Candidates are appended to the row's lists in global memory by QUADS
+// of adjacent columns: iff max(w0..w3) > thr, one predicated 16-byte store of the four values, whose
+// 6 low mantissa bits carry the quad's position and the gallery tile index (see "Candidate records"
+// below).  Nothing is ever pruned or re-ordered on the SM; the re-score kernel (score_exact.cuh)
+// selects the best 32 of a row's lists and certifies the result.  Bounds are shared between the 4
+// threads of a row through shared memory every other tile and between CTAs working on the same rows
+// through global memory (atomicMax on an order-preserving integer image of the float).  To warm the
+// bound before anything is appended, the segment holding a row's first gallery tile -- and whatever
+// segment a CTA sweeps first -- previews a few sample tiles of its range in threshold-only mode.
 //
 // Work decomposition: the (query tile, gallery tile) grid is linearised query-major and cut
 // into one contiguous range per CTA, balanced on the host by cost (tiles + sample tiles + segment
-// starts); a range is processed as at most a few "segments" (one query tile x a run of gallery tiles).
+// starts); a range is processed as at most a few "segments" (one query tile x a run of gallery
+// tiles), last segment first (segment_before).
 //
 // Roles (608 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
 // allocator, then stages cg tiles, warps 3..18 = epilogue (warp%4 selects the TMEM lane quarter =
@@ -31,7 +32,8 @@
 // Tile: 128 queries x 256 gallery rows, K = 256 as 4 k-blocks of 64 fp16 (128-byte swizzle).
 // The A (query) tile stays resident in shared memory for a whole segment; B (gallery)
 // k-blocks stream through a 4-stage ring; two 256-column TMEM accumulators alternate, and an
-// epilogue warp hands its accumulator back as soon as its 64 columns sit in registers.
+// epilogue warp hands its accumulator back as soon as its last 16-column load has landed (half-way
+// through its work on the tile).
 #pragma once
 #include <cstdint>
 #include <utility>
