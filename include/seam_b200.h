@@ -157,6 +157,19 @@ int seam_score_dense(seam_handle* h, const float* q, int Q, const float* g, int 
 int seam_rank_of_target(seam_handle* h, const float* q, int Q, const float* g, int G, const int32_t* target,
                         int32_t* out_rank, float* out_margin, void* stream);
 
+/* Same result as seam_rank_of_target (bit for bit: ranks are integers decided in the same fp32 direct
+ * form) through the tensor cores, for a PREPARED gallery (seam_prepare_gallery): the tcgen05 pass counts
+ * the items whose value exceeds the target's by more than the pass's error bound and nominates the items
+ * inside the band, a resolve kernel decides those in fp32, rows it cannot certify are ranked exhaustively
+ * (their number is returned in stats[0]).  This is the "rank = position in the full argsort" of
+ * evaluate_movingfashion.py:268-269 / evaluate_multiDF2.py:225-226 for every query at once, without a sort.
+ *   workspace: seam_rank_workspace_bytes(h, Q, G) bytes, 256-byte aligned; stats (4) int32 optional. */
+size_t seam_rank_workspace_bytes(const seam_handle* h, int Q, int G);
+int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const float* g, const void* g16,
+                                 const float* cg, const float* gstat, int G, const int32_t* target, int32_t* out_rank,
+                                 float* out_margin, int32_t* stats, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* Merge N per-shard top-k lists (after the all-gather) into one: lists are (N,Q,k)
  * contiguous; entries with idx < 0 are invalid.  Same ordering contract as seam_score_topk.
  * No reference counterpart (the reference ranks a single gallery). */

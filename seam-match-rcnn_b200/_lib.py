@@ -99,6 +99,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_score_dense.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     lib.seam_rank_of_target.restype = i32
     lib.seam_rank_of_target.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    lib.seam_rank_workspace_bytes.restype = sz
+    lib.seam_rank_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.seam_rank_of_target_prepared.restype = i32
+    lib.seam_rank_of_target_prepared.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.seam_upload_tracks.restype = i32
     lib.seam_upload_tracks.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.seam_merge_topk.restype = i32

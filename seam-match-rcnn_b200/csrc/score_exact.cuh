@@ -569,36 +569,196 @@ __global__ void __launch_bounds__(256) dense_logits_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------- rank of a target item
-// CTA per query: margin of the target, then count items ranking before it.
+// CTA per query: margin of the target, then count items ranking before it -- exhaustive, fp32 direct
+// form.  With a row list (count, rows) only those queries are processed (the rows the tensor-core
+// path below could not certify).
 __global__ void __launch_bounds__(256) rank_of_target_kernel(const float* __restrict__ q, int Q,
                                                              const float* __restrict__ g, int G,
                                                              const int32_t* __restrict__ target,
                                                              const float* __restrict__ fold,
+                                                             const int32_t* __restrict__ count,
+                                                             const int32_t* __restrict__ rows,
                                                              int32_t* __restrict__ out_rank,
                                                              float* __restrict__ out_margin) {
   __shared__ int cnt_s[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qi = blockIdx.x;
+  const Slice w0 = load_slice(fold + Fold::LAST_W, lane);
+  const Slice w1 = load_slice(fold + Fold::LAST_W + 256, lane);
+  const float b0 = fold[Fold::CONSTS + 5], b1 = fold[Fold::CONSTS + 6];
+  const int nrows = count ? *count : Q;
+  for (int e = blockIdx.x; e < nrows; e += gridDim.x) {
+    const int qi = count ? rows[e] : e;
+    const Slice qs = load_slice(q + (size_t)qi * 256, lane);
+    const int tj = target[qi];
+    float l0, l1;
+    pair_logits(qs, g + (size_t)tj * 256, w0, w1, b0, b1, lane, l0, l1);
+    const float dt = l1 - l0;
+    int cnt = 0;
+    for (int j = warp; j < G; j += 8) {
+      pair_logits(qs, g + (size_t)j * 256, w0, w1, b0, b1, lane, l0, l1);
+      if (wsort::ranks_before(l1 - l0, j, dt, tj)) ++cnt;
+    }
+    if (lane == 0) cnt_s[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += cnt_s[w];
+      out_rank[qi] = tot;
+      if (out_margin) out_margin[qi] = dt;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- rank of a target item, tensor-core path
+// rank_i = #{ j : (d_ij, j) ranks before (d_it, t) } without visiting every pair in fp32: the tcgen05 pass
+// (score_tc.cuh, VAR_RANK) counts the elements whose value exceeds the target's by more than its error
+// bound and appends the quads that hold an element inside the band; rank_resolve_kernel adds the exact
+// fp32 verdict for those.
+//
+// warp per query: exact margin of the target, its image v* in the space of the tensor-core values
+// (v = d - rq - db), and the band v* +- E with E >= |w - v| for every element near the band:
+// EPS_COEFF ||a_i|| max_j ||g_j||  (fp16 operands)  +  TAG_REL_ERR (|v*| + that)  (column tag)  +  fp32 slack.
+__global__ void __launch_bounds__(256) rank_prep_kernel(const float* __restrict__ q, int Q, const float* __restrict__ g,
+                                                        const int32_t* __restrict__ target,
+                                                        const float* __restrict__ fold, const float* __restrict__ rq,
+                                                        const float* __restrict__ anorm,
+                                                        const float* __restrict__ gstat, float* __restrict__ lo,
+                                                        float* __restrict__ hi, float* __restrict__ dtarget,
+                                                        int32_t* __restrict__ above, int nlists) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= Q) return;
   const Slice w0 = load_slice(fold + Fold::LAST_W, lane);
   const Slice w1 = load_slice(fold + Fold::LAST_W + 256, lane);
   const float b0 = fold[Fold::CONSTS + 5], b1 = fold[Fold::CONSTS + 6];
   const Slice qs = load_slice(q + (size_t)qi * 256, lane);
-  const int tj = target[qi];
   float l0, l1;
-  pair_logits(qs, g + (size_t)tj * 256, w0, w1, b0, b1, lane, l0, l1);
+  pair_logits(qs, g + (size_t)target[qi] * 256, w0, w1, b0, b1, lane, l0, l1);
   const float dt = l1 - l0;
-  int cnt = 0;
-  for (int j = warp; j < G; j += 8) {
-    pair_logits(qs, g + (size_t)j * 256, w0, w1, b0, b1, lane, l0, l1);
-    if (wsort::ranks_before(l1 - l0, j, dt, tj)) ++cnt;
+  for (int l = lane; l < nlists; l += 32) above[(size_t)qi * nlists + l] = 0;
+  if (lane == 0) {
+    const float vstar = dt - rq[qi] - fold[Fold::CONSTS + 4];
+    const float e0 = EPS_COEFF * anorm[qi] * gstat[0] + 1e-5f;
+    const float E = e0 + TAG_REL_ERR * (fabsf(vstar) + e0) + 4e-6f * (1.f + fabsf(dt) + fabsf(vstar));
+    lo[qi] = vstar - E;
+    hi[qi] = vstar + E;
+    dtarget[qi] = dt;
   }
-  if (lane == 0) cnt_s[warp] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0;
-    for (int w = 0; w < 8; ++w) tot += cnt_s[w];
-    out_rank[qi] = tot;
-    if (out_margin) out_margin[qi] = dt;
+}
+
+struct RankResolveParams {
+  const float* q;
+  const float* g;
+  const float* fold;
+  const uint2* rowbuf;
+  const uint32_t* rowcnt;
+  const uint32_t* rowflag;
+  const int32_t* above;      // (Q,nlists)
+  const float* lo;
+  const float* hi;
+  const float* dtarget;
+  const float* rq;
+  const float* gstat;
+  const int32_t* target;
+  int Q, G, nlists, CAP;
+  int32_t* out_rank;
+  float* out_margin;         // optional
+  int32_t* counters;         // [0] rows for the exhaustive kernel, [1] query overflow flag
+  int32_t* fallback_rows;
+};
+constexpr int RANK_CAND = 96;    // in-band candidates gathered before they are decided (+ 128 of headroom per round)
+
+// warp per query: certain count from the tensor-core pass + exact verdicts for the elements in the band
+// (a target in the bulk of the ranking has about 1 % of the gallery inside its band; one near the top,
+// the case the eval cares about, a handful)
+__global__ void __launch_bounds__(256) rank_resolve_kernel(const RankResolveParams p) {
+  __shared__ uint2 cand[8][RANK_CAND + 128];   // {approximate value, gallery row}
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= p.Q) return;
+  const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
+  bool ok = !overflow && p.rowflag[qi] == 0;
+  const float lo = p.lo[qi], hi = p.hi[qi], dt = p.dtarget[qi];
+  const int tj = p.target[qi];
+  const int capq = p.CAP / 2;
+  const uint4* rowq = reinterpret_cast<const uint4*>(p.rowbuf) + (size_t)qi * p.nlists * capq;
+  uint2* cb = cand[warp];
+  const Slice qs = load_slice(p.q + (size_t)qi * 256, lane);
+  const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
+  const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
+  const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
+  const float eps = 0.5f * (hi - lo);
+  const float shift = p.rq[qi] + p.fold[Fold::CONSTS + 4];
+  int total = 0, fill = 0, exact_before = 0;
+  // decides the buffered candidates in exact fp32, four gallery rows per step
+  auto decide = [&]() {
+    __syncwarp();
+    for (int c0 = 0; c0 < fill; c0 += 4) {
+      Slice gs[4];
+      uint2 ce[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ce[u] = cb[min(c0 + u, fill - 1)];
+        gs[u] = load_slice(p.g + (size_t)ce[u].y * 256, lane);
+      }
+      float part[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sqdiff_dot2(qs, gs[u], w0, w1, part[2 * u], part[2 * u + 1]);
+      const float tot = ptx::treduce<8>(part, lane);   // lane l: total of part[l % 8]
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float l0v = __shfl_sync(ptx::FULL_MASK, tot, 2 * u) + b0;
+        const float l1v = __shfl_sync(ptx::FULL_MASK, tot, 2 * u + 1) + b1;
+        const float d = l1v - l0v;
+        if (c0 + u < fill) {
+          if (wsort::ranks_before(d, (int)ce[u].y, dt, tj)) ++exact_before;
+          // observed error of the tensor-core value against the bound the band was built with
+          if (!(fabsf(d - (__uint_as_float(ce[u].x) + shift)) <= eps)) ok = false;
+        }
+      }
+    }
+    fill = 0;
+    __syncwarp();
+  };
+  for (int l0 = 0; l0 < p.nlists && ok; l0 += 32) {
+    const int my_l = l0 + lane;
+    const uint32_t my_n = my_l < p.nlists ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
+    total += my_l < p.nlists ? p.above[(size_t)qi * p.nlists + my_l] : 0;
+    if (__any_sync(ptx::FULL_MASK, my_n > (uint32_t)capq)) ok = false;
+    const int nl = min(32, p.nlists - l0);
+    for (int j = 0; j < nl && ok; ++j) {
+      const int n = (int)__shfl_sync(ptx::FULL_MASK, my_n, j);
+      const uint4* lp = rowq + (size_t)(l0 + j) * capq;
+      for (int base = 0; base < n && ok; base += 32) {
+        const bool have = base + lane < n;
+        const uint4 rec = have ? __ldcs(lp + base + lane) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t wv[4] = {rec.x, rec.y, rec.z, rec.w};
+        const uint32_t tile = (rec.y & 63u) | ((rec.z & 63u) << 6) | ((rec.w & 63u) << 12);
+        const uint32_t col = tile * 256u + (uint32_t)(j & 3) * 64u + (rec.x & 63u) * 4u;
+#pragma unroll
+        for (int el = 0; el < 4; ++el) {
+          const float ev = __uint_as_float(wv[el]);
+          const bool in_band = have && ev > lo && !(ev > hi);
+          const uint32_t mask = __ballot_sync(ptx::FULL_MASK, in_band);
+          if (mask == 0u) continue;
+          if (in_band) cb[fill + __popc(mask & ((1u << lane) - 1u))] = make_uint2(wv[el], col + el);
+          fill += __popc(mask);
+        }
+        if (fill >= RANK_CAND) decide();
+      }
+    }
+  }
+  total = __reduce_add_sync(ptx::FULL_MASK, total);
+  if (ok && fill > 0) decide();
+  if (lane == 0) {
+    if (ok) {
+      p.out_rank[qi] = total + exact_before;
+      if (p.out_margin) p.out_margin[qi] = dt;
+    } else {
+      const int slot = atomicAdd(p.counters, 1);
+      p.fallback_rows[slot] = qi;
+    }
   }
 }
 

@@ -69,6 +69,7 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory li
 static_assert(OFF_CG % 16 == 0 && OFF_THRX % 16 == 0 && OFF_CMD % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
 constexpr int MAX_GRID = 160;          // one persistent CTA per SM
+constexpr int VAR_RANK = 6;            // kernel variant: rank of one designated gallery item per query
 struct Params {
   int Q, G, num_mtiles, ntiles_n;
   long long total_tiles;
@@ -84,6 +85,11 @@ struct Params {
   float* gmax;                // (Q, P, 4, 16) final group maxima of each thread (disjoint column groups)
   unsigned long long* cta_ns; // (grid, 2) optional: {duration in ns, segments} per CTA (developer diagnostics)
   int tb[MAX_GRID + 1];       // CTA b sweeps the linearised tiles [tb[b], tb[b+1]) (cost-balanced on the host)
+  // rank-of-target variant (VAR_RANK): per-row band (lo, hi] around the target's value and, per sub-list,
+  // the number of elements certainly above it
+  const float* rank_lo;       // (Q)
+  const float* rank_hi;       // (Q)
+  int32_t* rank_above;        // (Q, P, 4)
 };
 
 // the CTA whose (non-empty) range contains tile t: the largest b with tb[b] <= t
@@ -289,6 +295,44 @@ __device__ __forceinline__ void filter16(const uint32_t (&r)[16], const float* c
   }
 }
 
+// Rank-of-target variant of the filter.  The row's band (lo, hi] brackets the target item's value by the
+// error bound of this pass: an element above hi certainly ranks before the target (counted here, one
+// compare + one predicated add), an element at or below lo certainly does not, and quads holding an
+// element inside the band are appended for the resolve kernel to decide in exact fp32.
+__device__ __forceinline__ void filter16_rank(const uint32_t (&r)[16], const float* cgp, uint64_t& wp, uint32_t& above,
+                                              float lo_or_inf, float hi, uint32_t keep, const TileTags& tg,
+                                              int q0) {
+  float cgv[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const float4 g4 = *reinterpret_cast<const float4*>(cgp + c4 * 4);
+    cgv[c4 * 4 + 0] = g4.x;
+    cgv[c4 * 4 + 1] = g4.y;
+    cgv[c4 * 4 + 2] = g4.z;
+    cgv[c4 * 4 + 3] = g4.w;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float w[4], t[4];
+    w[0] = tagged_reg(r[4 * q + 0], cgv[4 * q + 0], keep, (uint32_t)(q0 + q));
+    w[1] = tagged_reg(r[4 * q + 1], cgv[4 * q + 1], keep, tg.t1);
+    w[2] = tagged_reg(r[4 * q + 2], cgv[4 * q + 2], keep, tg.t2);
+    w[3] = tagged_reg(r[4 * q + 3], cgv[4 * q + 3], keep, tg.t3);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      asm("{\n"
+          ".reg .pred p;\n"
+          "setp.gt.f32 p, %2, %3;\n"
+          "@p add.u32 %0, %0, 1;\n"
+          "selp.f32 %1, 0fFF800000, %2, p;\n"      // elements above the band do not make a quad uncertain
+          "}\n"
+          : "+r"(above), "=f"(t[e])
+          : "f"(w[e]), "f"(hi));
+    const float m = fmaxf(max3(t[0], t[1], t[2]), t[3]);
+    append_quad<0>(wp, m, lo_or_inf, w[0], w[1], w[2], w[3]);
+  }
+}
+
 template <int VAR>   // 0 = product; 2..4 = developer diagnostics (partial epilogues, wrong results)
 __global__ void __launch_bounds__(THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -472,8 +516,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t room = (uint32_t)p.CAP * 8u - (uint32_t)(QCOLS / 4) * 16u;
     // kept in a register (opaque to ptxas) so that the quad tag can be the LOP3's immediate operand
     const uint32_t keep = ~TAG_MASK | (uint32_t)(p.Q >> 31);
-    float thr = INFINITY;
+    float thr = INFINITY;                    // VAR_RANK: the band's lower edge
     float gm[GROUPS];
+    float rank_hi = INFINITY;                // VAR_RANK only
+    uint32_t above = 0;
     for (;;) {
       ptx::mbar_wait(&cg_full[acc], aphase);
       const int4 cmd = *reinterpret_cast<const int4*>(cmd_s + acc * 4);
@@ -485,7 +531,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const size_t li = slot_ok ? ((size_t)grow * p.P + cmd.w) * NQ + cq : 0;   // this thread's sub-list
         wp = reinterpret_cast<uint64_t>(p.rowbuf + li * (size_t)p.CAP);
         wlo_begin = (uint32_t)wp;            // only the low address word ever changes (no 4 GiB straddle)
-        thr = row_ok ? ptx::ordered_to_float(__ldcg(p.thr_global + grow)) : INFINITY;
+        if constexpr (VAR == VAR_RANK) {
+          thr = row_ok ? p.rank_lo[grow] : INFINITY;
+          rank_hi = row_ok ? p.rank_hi[grow] : INFINITY;
+          above = 0;
+        } else {
+          thr = row_ok ? ptx::ordered_to_float(__ldcg(p.thr_global + grow)) : INFINITY;
+        }
         st = (row_ok ? ST_ROW : 0u) | (slot_ok ? ST_SLOT : (ST_CLOSED | ST_LOSSY)) | ((uint32_t)(cmd.w & 0xffff) << 8);
         itile = 0;
 #pragma unroll
@@ -518,10 +570,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tg.t3 = ((uint32_t)cmd.x >> (2 * TAG_BITS)) & TAG_MASK;
         ptx::tmem_ld_wait_x16(ra);
         ptx::tmem_ld_x16(taddr + 16, rb);
-        filter16<VAR, 0, 0>(ra, cgp, gm, wp, cmp, keep, tg);
+        if constexpr (VAR == VAR_RANK) filter16_rank(ra, cgp, wp, above, cmp, rank_hi, keep, tg, 0);
+        else filter16<VAR, 0, 0>(ra, cgp, gm, wp, cmp, keep, tg);
         ptx::tmem_ld_wait_x16(rb);
         ptx::tmem_ld_x16(taddr + 32, ra);
-        filter16<VAR, 4, 4>(rb, cgp + 16, gm, wp, cmp, keep, tg);
+        if constexpr (VAR == VAR_RANK) filter16_rank(rb, cgp + 16, wp, above, cmp, rank_hi, keep, tg, 4);
+        else filter16<VAR, 4, 4>(rb, cgp + 16, gm, wp, cmp, keep, tg);
         ptx::tmem_ld_wait_x16(ra);
         ptx::tmem_ld_x16(taddr + 48, rb);
         // The MMA of the tile after next cannot start before the slowest of the 16 warps has read its
@@ -531,14 +585,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
-        filter16<VAR, 8, 8>(ra, cgp + 32, gm, wp, cmp, keep, tg);
-        filter16<VAR, 12, 12>(rb, cgp + 48, gm, wp, cmp, keep, tg);
+        if constexpr (VAR == VAR_RANK) {
+          filter16_rank(ra, cgp + 32, wp, above, cmp, rank_hi, keep, tg, 8);
+          filter16_rank(rb, cgp + 48, wp, above, cmp, rank_hi, keep, tg, 12);
+        } else {
+          filter16<VAR, 8, 8>(ra, cgp + 32, gm, wp, cmp, keep, tg);
+          filter16<VAR, 12, 12>(rb, cgp + 48, gm, wp, cmp, keep, tg);
+        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&cg_empty[acc]);
         // share the bound: each of the row's 4 threads vouches for 8 distinct items at or above the
         // 8th largest of its 16 group maxima (re-derived every other tile), the smallest of the four
         // values therefore for 32
         const bool seed_end = (cmd.y & CMD_SEED_END) != 0;
+        if constexpr (VAR != VAR_RANK) {
         if ((itile & 1) || seed_end) {
           thr_x[R * NQ + cq] = eighth_largest_of_16(gm);
           // After the sample sweep the four warps of a row meet once, so that the first appended
@@ -551,20 +611,25 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t old = atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
           thr = fmaxf(thr, ptx::ordered_to_float(old));
         }
+        }
         ++itile;
         // ---- segment end: publish the list length, the bound and the loss flag
         if ((cmd.y & CMD_SEG_END) && (st & ST_ROW)) {
           if (st & ST_SLOT) {
             const size_t li = ((size_t)grow * p.P + (st >> 8)) * NQ + cq;
             p.rowcnt[li] = ((uint32_t)wp - wlo_begin) >> 4;   // quads
-            float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
-            gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
-            gd[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
-            gd[2] = make_float4(gm[8], gm[9], gm[10], gm[11]);
-            gd[3] = make_float4(gm[12], gm[13], gm[14], gm[15]);
+            if constexpr (VAR == VAR_RANK) {
+              p.rank_above[li] = (int32_t)above;
+            } else {
+              float4* gd = reinterpret_cast<float4*>(p.gmax + li * GROUPS);
+              gd[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
+              gd[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+              gd[2] = make_float4(gm[8], gm[9], gm[10], gm[11]);
+              gd[3] = make_float4(gm[12], gm[13], gm[14], gm[15]);
+            }
           }
           if (st & ST_LOSSY) atomicOr(p.rowflag + grow, 1u);
-          atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
+          if constexpr (VAR != VAR_RANK) atomicMax(p.thr_global + grow, ptx::float_to_ordered(thr));
         }
       }
       if (++acc == 2) {

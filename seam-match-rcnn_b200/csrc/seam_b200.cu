@@ -176,6 +176,8 @@ int seam_create(seam_handle** out, int device) {
   cudaFuncSetAttribute(score::score_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(score::score_topk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(score::score_topk_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
+  cudaFuncSetAttribute(score::score_topk_kernel<score::VAR_RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)aggw::smem_bytes<4>());
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -432,7 +434,7 @@ static int env_int(const char* name, int dflt) {
 // range per CTA (score_tc.cuh).  A query tile's gallery sweep is therefore shared by at most P
 // CTAs ("pieces"); each piece owns 4 candidate sub-lists per row (one per epilogue thread of
 // the row) of CAP entries, CAP >= 3 times the expected number of appends.
-static ScorePlan plan_score(int num_sms, int Q, int G) {
+static ScorePlan plan_score(int num_sms, int Q, int G, int nseed_override = -1) {
   ScorePlan s;
   s.num_mtiles = (Q + score::BM - 1) / score::BM;
   s.ntiles_n = (G + score::BN - 1) / score::BN;
@@ -445,7 +447,7 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
     if (cap_grid > 0 && cap_grid < s.grid) s.grid = cap_grid;
   }
   if (s.grid > score::MAX_GRID) s.grid = score::MAX_GRID;
-  s.nseed = env_int("SEAM_SCORE_NSEED", 4);
+  s.nseed = nseed_override >= 0 ? nseed_override : env_int("SEAM_SCORE_NSEED", 4);
   // Cost-balanced contiguous ranges.  A tile costs 1; a segment start costs SEG_COST (query tile load,
   // epilogue hand-over); a segment that holds its row's first gallery tile -- or is all a CTA has --
   // also sweeps min(nseed, length) threshold-only sample tiles (score_tc.cuh, segment_before).  walk()
@@ -530,6 +532,12 @@ static ScorePlan plan_score(int num_sms, int Q, int G) {
     need = 16.0 * 3.0 * (64.0 + 32.0 * log(T));
   }
   if (need > T * tile_bytes) need = T * tile_bytes;          // a thread cannot append more than it sees
+  if (nseed_override == 0) {
+    // rank-of-target variant: a thread appends the quads holding an element inside the band around the
+    // target's value -- about 1-2 % of its columns for a target in the bulk of the ranking; budget 6 %
+    const double band = 0.06 * T * score::QCOLS * 16.0;
+    if (band > need) need = band;
+  }
   need += tile_bytes;                                        // a list closes one tile before it is full
   int cap = 2 * score::QCOLS;                                // 8-byte units; power of two: a sub-list is aligned to its size
   while (cap * 8 < (int)need && cap < 8192) cap *= 2;
@@ -655,6 +663,9 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.rowflag = rowflag;
   sp.rowbuf = rowbuf;
   sp.gmax = gmax;
+  sp.rank_lo = nullptr;
+  sp.rank_hi = nullptr;
+  sp.rank_above = nullptr;
   // developer diagnostics: SEAM_DEBUG_CTA_NS=1 records per-CTA durations at the tail of the fallback-row list
   sp.cta_ns = (env_int("SEAM_DEBUG_CTA_NS", 0) && (size_t)Q * 4 >= 8192)
                   ? reinterpret_cast<unsigned long long*>(ws + s.off_rows + (((size_t)Q * 4 - 4096) & ~(size_t)7))
@@ -744,9 +755,122 @@ int seam_rank_of_target(seam_handle* h, const float* q, int Q, const float* g, i
   if (!q || !g || !target || !out_rank) return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_of_target: null pointer");
   if (!aligned16(q) || !aligned16(g)) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_of_target: 16-byte alignment");
   DeviceGuard guard(h->device);
-  exact::rank_of_target_kernel<<<Q, 256, 0, static_cast<cudaStream_t>(stream_)>>>(q, Q, g, G, target, h->fold,
-                                                                                   out_rank, out_margin);
+  exact::rank_of_target_kernel<<<Q, 256, 0, static_cast<cudaStream_t>(stream_)>>>(q, Q, g, G, target, h->fold, nullptr,
+                                                                                   nullptr, out_rank, out_margin);
   SEAM_LAUNCHED(h, "rank_of_target_kernel");
+  return SEAM_OK;
+}
+
+size_t seam_rank_workspace_bytes(const seam_handle* h, int Q, int G) {
+  if (!h || Q <= 0 || G <= 0) return 256;
+  return plan_score(h->num_sms, Q, G, 0).total;
+}
+
+// Tensor-core path: prepare queries -> exact target margins + bands -> score_topk_kernel<VAR_RANK> (counts
+// what is certainly above, appends what is inside the band) -> rank_resolve_kernel -> exhaustive kernel for
+// the rows that could not be certified.  The workspace is laid out like seam_score_topk's (no sample
+// tiles); the band, the target margins and the per-sub-list counts live in its group-maxima region.
+int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const float* g, const void* g16,
+                                 const float* cg, const float* gstat, int G, const int32_t* target, int32_t* out_rank,
+                                 float* out_margin, int32_t* stats, void* workspace, size_t workspace_bytes,
+                                 void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_rank_of_target_prepared: scorer weights not loaded");
+  if (Q < 0 || G <= 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_of_target_prepared: bad size");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  if (stats) SEAM_CUDA(h, cudaMemsetAsync(stats, 0, 16, stream));
+  if (Q == 0) return SEAM_OK;
+  if (!q || !g || !g16 || !cg || !gstat || !target || !out_rank || !workspace)
+    return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_of_target_prepared: null pointer");
+  if (!aligned16(q) || !aligned16(g) || !aligned16(g16) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_of_target_prepared: q/g/g16 need 16-byte, workspace 256-byte alignment");
+  const ScorePlan s = plan_score(h->num_sms, Q, G, 0);
+  if (s.ntiles_n > (1 << 18))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_of_target_prepared: G=%d exceeds the 2^26 gallery rows one shard may hold", G);
+  if (workspace_bytes < s.total)
+    return fail(h, SEAM_ERR_STATE, "seam_rank_of_target_prepared: workspace too small (%zu < %zu)", workspace_bytes, s.total);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  __half* a16 = reinterpret_cast<__half*>(ws + s.off_a16);
+  float* rq = reinterpret_cast<float*>(ws + s.off_rq);
+  float* anorm = reinterpret_cast<float*>(ws + s.off_anorm);
+  uint32_t* thr = reinterpret_cast<uint32_t*>(ws + s.off_thr);
+  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(ws + s.off_rowcnt);
+  float* gmax = reinterpret_cast<float*>(ws + s.off_gmax);
+  uint32_t* rowflag = reinterpret_cast<uint32_t*>(ws + s.off_rowflag);
+  uint2* rowbuf = reinterpret_cast<uint2*>(align_up(reinterpret_cast<uintptr_t>(ws + s.off_rowbuf), (size_t)s.CAP * 8));
+  int32_t* counters = reinterpret_cast<int32_t*>(ws + s.off_cnt);
+  int32_t* frows = reinterpret_cast<int32_t*>(ws + s.off_rows);
+  const int nlists = s.P * score::NQ;
+  // the group-maxima region (Q x nlists x 16 words) is free in this variant
+  int32_t* above = reinterpret_cast<int32_t*>(gmax);
+  float* lo = gmax + (size_t)Q * nlists;
+  float* hi = lo + Q;
+  float* dtarget = hi + Q;
+
+  exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt, nlists, gmax,
+                                                             rowflag, counters);
+  SEAM_LAUNCHED(h, "prep_queries_kernel");
+  exact::rank_prep_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, g, target, h->fold, rq, anorm, gstat, lo, hi, dtarget,
+                                                          above, nlists);
+  SEAM_LAUNCHED(h, "rank_prep_kernel");
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = encode_map_fp16_rows(h, &tmA, a16, Q, score::BM)) != SEAM_OK) return rc;
+  if ((rc = encode_map_fp16_rows(h, &tmB, g16, G, score::BN)) != SEAM_OK) return rc;
+  score::Params sp;
+  sp.Q = Q;
+  sp.G = G;
+  sp.num_mtiles = s.num_mtiles;
+  sp.ntiles_n = s.ntiles_n;
+  sp.total_tiles = s.total_tiles;
+  sp.P = s.P;
+  sp.CAP = s.CAP;
+  sp.nseed = 0;
+  sp.mode = score::VAR_RANK;
+  for (int b = 0; b <= s.grid; ++b) sp.tb[b] = s.tb[b];
+  sp.cg = cg;
+  sp.thr_global = thr;
+  sp.rowcnt = rowcnt;
+  sp.rowflag = rowflag;
+  sp.rowbuf = rowbuf;
+  sp.gmax = gmax;
+  sp.cta_ns = nullptr;
+  sp.rank_lo = lo;
+  sp.rank_hi = hi;
+  sp.rank_above = above;
+  score::score_topk_kernel<score::VAR_RANK><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+  SEAM_LAUNCHED(h, "score_topk_kernel<rank>");
+
+  exact::RankResolveParams rp;
+  rp.q = q;
+  rp.g = g;
+  rp.fold = h->fold;
+  rp.rowbuf = rowbuf;
+  rp.rowcnt = rowcnt;
+  rp.rowflag = rowflag;
+  rp.above = above;
+  rp.lo = lo;
+  rp.hi = hi;
+  rp.dtarget = dtarget;
+  rp.rq = rq;
+  rp.gstat = gstat;
+  rp.target = target;
+  rp.Q = Q;
+  rp.G = G;
+  rp.nlists = nlists;
+  rp.CAP = s.CAP;
+  rp.out_rank = out_rank;
+  rp.out_margin = out_margin;
+  rp.counters = counters;
+  rp.fallback_rows = frows;
+  exact::rank_resolve_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(rp);
+  SEAM_LAUNCHED(h, "rank_resolve_kernel");
+  exact::rank_of_target_kernel<<<2 * h->num_sms, 256, 0, stream>>>(q, Q, g, G, target, h->fold, counters, frows, out_rank,
+                                                                  out_margin);
+  SEAM_LAUNCHED(h, "rank_of_target_kernel");
+  if (stats) SEAM_CUDA(h, cudaMemcpyAsync(stats, counters, 4, cudaMemcpyDeviceToDevice, stream));
   return SEAM_OK;
 }
 

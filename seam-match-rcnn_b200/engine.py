@@ -236,21 +236,37 @@ class SeamEngine:
                                                x5.data_ptr(), self._stream()))
         return x5
 
-    def rank_of_target(self, q: torch.Tensor, g: torch.Tensor, target: torch.Tensor
-                       ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Rank (0 = best) of gallery row target[i] for query i: evaluate_movingfashion.py:268-269."""
-        q, g = self._f32(q, "queries"), self._f32(g, "gallery")
+    def rank_of_target(self, q: torch.Tensor, g, target: torch.Tensor, return_stats: bool = False):
+        """Rank (0 = best) of gallery row target[i] for query i: evaluate_movingfashion.py:268-269.
+
+        ``g`` is either a ``(G,256)`` tensor -- exhaustive fp32 kernel -- or a ``PreparedGallery`` -- the
+        tensor-core path (count what is certainly above the target, decide the rest in fp32); both give
+        the same integers.  Returns (rank int32 (Q,), target margin fp32 (Q,)[, stats])."""
+        q = self._f32(q, "queries")
+        prepared = isinstance(g, PreparedGallery)
+        gm = g.g if prepared else self._f32(g, "gallery")
         t32 = target.to(device=self.device, dtype=torch.int32).contiguous()
-        Q = q.shape[0]
+        Q, G = q.shape[0], gm.shape[0]
         if t32.shape != (Q,):
             raise ValueError("target must have one gallery row per query")
-        if Q and (int(t32.min()) < 0 or int(t32.max()) >= g.shape[0]):
+        if Q and (int(t32.min()) < 0 or int(t32.max()) >= G):
             raise ValueError("target index out of range")
         rank = torch.empty((Q,), dtype=torch.int32, device=self.device)
         margin = torch.empty((Q,), dtype=torch.float32, device=self.device)
-        self._check(self._lib.seam_rank_of_target(self._h, q.data_ptr(), Q, g.data_ptr(), g.shape[0],
-                                                  t32.data_ptr(), rank.data_ptr(), margin.data_ptr(),
-                                                  self._stream()))
+        stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        if prepared and Q > 0:
+            nbytes = int(self._lib.seam_rank_workspace_bytes(self._h, Q, G))
+            ws = self._workspace("score", nbytes)
+            self._check(self._lib.seam_rank_of_target_prepared(
+                self._h, q.data_ptr(), Q, gm.data_ptr(), g.g16.data_ptr(), g.cg.data_ptr(), g.gstat.data_ptr(), G,
+                t32.data_ptr(), rank.data_ptr(), margin.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(),
+                self._stream()))
+        else:
+            self._check(self._lib.seam_rank_of_target(self._h, q.data_ptr(), Q, gm.data_ptr(), G,
+                                                      t32.data_ptr(), rank.data_ptr(), margin.data_ptr(),
+                                                      self._stream()))
+        if return_stats:
+            return rank, margin, stats
         return rank, margin
 
     def upload_tracks(self, seq_host: torch.Tensor, lo: int, hi: int) -> torch.Tensor:

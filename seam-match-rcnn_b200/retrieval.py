@@ -206,7 +206,7 @@ def evaluate_aggregated(engine: SeamEngine, seq, mask, gallery: torch.Tensor, ta
     gal = engine.prepare_gallery(gallery)
     kmax = min(max(k_thresholds), 32)
     sc, mg, ix = engine.score_topk(q, gal, kmax)
-    ranks, _ = engine.rank_of_target(q, gal.g, target)
+    ranks, _ = engine.rank_of_target(q, gal, target)
     r = ranks.cpu()
     hits = [int((r < k).sum()) for k in k_thresholds]
     n = max(1, q.shape[0])
@@ -244,8 +244,8 @@ def evaluate_products(engine: SeamEngine, frame_desc: torch.Tensor, frame_produc
     ``frame_desc (N,256)`` are the match features of the tracked boxes, ``frame_product (N,)`` the product
     (0..P-1) each belongs to, ``shop_desc (G,256)`` / ``shop_aggr (G,256)`` the shop boxes' match features
     and aggregator descriptors, ``target (P,)`` each product's shop row; ``seq`` / ``mask`` the aggregator
-    input of the P tracks.  Ranks come from the fp32 direct-form kernel (``seam_rank_of_target``), i.e. the
-    position the reference reads out of its full argsort, without sorting.  The reference runs rows 0-2 in
+    input of the P tracks.  Ranks come from ``seam_rank_of_target_prepared`` (tensor-core count + fp32 verdicts near the target), i.e.
+    the position the reference reads out of its full argsort, without sorting.  The reference runs rows 0-2 in
     numpy fp16 (:82-100); these are the fp32 values of the same formulas.
     The average / maximum *distance* fusions (:294-316) reduce a (frames x gallery) score matrix per product
     and are not covered here."""
@@ -258,14 +258,15 @@ def evaluate_products(engine: SeamEngine, frame_desc: torch.Tensor, frame_produc
     ks = list(k_thresholds)
 
     engine.load_scorer(*frame_last)
-    fr, _ = engine.rank_of_target(frame_desc, shop_desc, target[fp])
+    shop = engine.prepare_gallery(shop_desc)             # operands depend on the scorer just loaded
+    fr, _ = engine.rank_of_target(frame_desc, shop, target[fp])
     big = torch.iinfo(torch.int32).max
     best = torch.full((P,), big, dtype=torch.int32, device=dev).scatter_reduce(0, fp, fr, "amin")
     cnt = torch.zeros((P,), dtype=torch.float32, device=dev).index_add_(0, fp, torch.ones_like(fr, dtype=torch.float32))
     avg = torch.zeros((P, frame_desc.shape[1]), dtype=torch.float32, device=dev).index_add_(0, fp, frame_desc)
     has = cnt > 0
     avg = avg / cnt.clamp(min=1.0)[:, None]
-    ar, _ = engine.rank_of_target(avg, shop_desc, target)
+    ar, _ = engine.rank_of_target(avg, shop, target)
     ar = torch.where(has, ar, torch.full_like(ar, big))
 
     engine.load_scorer(*aggr_last)

@@ -212,6 +212,53 @@ def test_topk_fp16_overflow_is_safe(weights, engine):
     assert_topk_matches(ix, mg, sc, so.logit_margin(x5), so.match_scores(x5), 5, tol=2e-2)
 
 
+# ----------------------------------------------------------------------------- rank of the target item
+@pytest.mark.parametrize("Q,G", [(1, 1), (5, 33), (130, 257), (300, 5000), (97, 26000), (640, 12000)])
+def test_rank_of_target_tensor_core_path(Q, G, weights, engine):
+    """evaluate_movingfashion.py:268-269 for every query at once: the tensor-core path (count what is
+    certainly above the target, decide the band in fp32) must give the integers of the exhaustive fp32
+    kernel and of the oracle's argsort, for targets anywhere in the ranking."""
+    rs = np.random.RandomState(Q * 31 + G)
+    q = torch.from_numpy(rs.randn(Q, 256).astype(np.float32))
+    g = so.synth_gallery(G, seed=Q + G, planted=q)
+    target = torch.from_numpy(rs.randint(0, G, size=Q).astype(np.int64))
+    target[::3] = torch.arange(Q)[::3] % G                    # planted items: ranks near the top
+    gal = engine.prepare_gallery(g.to(DEV))
+    r_fast, m_fast, stats = engine.rank_of_target(q.to(DEV), gal, target, return_stats=True)
+    r_slow, m_slow = engine.rank_of_target(q.to(DEV), g.to(DEV), target)
+    assert torch.equal(r_fast, r_slow) and torch.equal(m_fast, m_slow)
+    assert int(stats[0]) <= max(1, Q // 20), "nearly every row should be certified by the tensor-core path"
+    x5 = so.pair_logits(q, g, weights, chunk=64)
+    ref = so.rank_of_target(x5, target)
+    d = so.logit_margin(x5)
+    bad = (r_fast.cpu().long() != ref).nonzero().flatten()
+    for i in bad.tolist():                                     # only ties inside the stated tolerance may differ
+        dt = d[i, target[i]]
+        lo, hi = sorted((int(r_fast[i]), int(ref[i])))
+        near = ((d[i] - dt).abs() <= TOL_LOGIT).sum()
+        assert hi - lo <= int(near), (i, lo, hi, int(near))
+
+
+def test_rank_of_target_crowded_band_and_overflow(weights, engine):
+    """Near-identical gallery items all fall inside the error band around the target: every one of them
+    is decided in exact fp32 (streamed through the resolve kernel) -- same integers as the exhaustive
+    kernel; values beyond the fp16 range send every row to the exhaustive kernel."""
+    rs = np.random.RandomState(12)
+    q = torch.from_numpy(rs.randn(24, 256).astype(np.float32))
+    base = torch.from_numpy(rs.randn(1, 256).astype(np.float32))
+    g = base + 1e-4 * torch.from_numpy(rs.randn(3000, 256).astype(np.float32))
+    target = torch.from_numpy(rs.randint(0, 3000, size=24).astype(np.int64))
+    gal = engine.prepare_gallery(g.to(DEV))
+    r_fast, _, stats = engine.rank_of_target(q.to(DEV), gal, target, return_stats=True)
+    r_slow, _ = engine.rank_of_target(q.to(DEV), g.to(DEV), target)
+    assert torch.equal(r_fast, r_slow)
+    g[7, 3] = 1.0e5                                            # fp16 overflow: every row takes the exhaustive kernel
+    gal = engine.prepare_gallery(g.to(DEV))
+    r_fast, _, stats = engine.rank_of_target(q.to(DEV), gal, target, return_stats=True)
+    r_slow, _ = engine.rank_of_target(q.to(DEV), g.to(DEV), target)
+    assert int(stats[0]) == 24 and torch.equal(r_fast, r_slow)
+
+
 def test_topk_empty(engine):
     q = torch.randn(5, 256, device=DEV)
     gal = engine.prepare_gallery(torch.zeros(0, 256, device=DEV))
