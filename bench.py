@@ -217,7 +217,22 @@ def run_ours(args):
     per = qhi - qlo
     even = (Q % world == 0)
 
+    # N > 1: both exchange steps (descriptors, candidate lists) as P2P writes into symmetric memory +
+    # device-side barriers (retrieval.PeerExchange) -- capturable, so the whole step is one graph; the
+    # NCCL all-gather path below stays as the fallback (SEAM_BENCH_PEER=0 or no symmetric memory).
+    peer, peer_note = None, ""
+    if world > 1 and even and os.environ.get("SEAM_BENCH_PEER", "1") != "0":
+        try:
+            peer = pkg.PeerExchange(eng, Q, k)
+        except Exception as ex:                      # noqa: BLE001 -- any failure means: keep NCCL
+            peer_note = f" (symmetric memory unavailable: {type(ex).__name__})"
+
     def hot_path(seq, mask, gal):
+        if peer is not None:
+            peer.begin_step()
+            eng.aggregate(seq, mask, out=peer.rows_out(qlo, qhi))
+            eng.score_topk(peer.share_rows(qlo, qhi), gal, k, out=peer.lists_out())
+            return eng.merge_topk(*peer.share_lists())
         q = eng.aggregate(seq, mask)
         if world > 1:
             if even:                                   # one collective on a preallocated (Q,256) buffer
@@ -239,7 +254,7 @@ def run_ours(args):
     # The step is launch-bound at this size (a dozen kernels of 5-200 us): replay it as one CUDA
     # graph.  SEAM_BENCH_GRAPH=0 falls back to eager launches.
     # (N > 1 stays eager: NCCL collectives inside a captured graph hung on this stack.)
-    use_graph = os.environ.get("SEAM_BENCH_GRAPH", "1") != "0" and world == 1
+    use_graph = os.environ.get("SEAM_BENCH_GRAPH", "1") != "0" and (world == 1 or peer is not None)
     graph = None
     if use_graph:
         side = torch.cuda.Stream(device=dev)
@@ -252,14 +267,14 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             graph_out = hot_path(seq_d, mask_d, gallery)
 
     # N > 1: the collectives stay eager, the kernels between them are replayed as three graphs
     # (aggregate | prepare + score + re-score | merge) so that the host enqueues 8 items per step
     # instead of ~25.
     seg = None
-    if world > 1 and even and os.environ.get("SEAM_BENCH_GRAPH", "1") != "0":
+    if world > 1 and even and graph is None and os.environ.get("SEAM_BENCH_GRAPH", "1") != "0":
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -321,7 +336,14 @@ def run_ours(args):
         g = eng.prepare_gallery(g_d, index_offset=rank * Gs)
         g_d.record_stream(main)
         parts = [q_c for _, _, q_c in track_stream.chunks(seq_h, mask_h)]
-        if world > 1:
+        if world > 1 and peer is not None:
+            peer.begin_step()
+            peer.rows_out(qlo, qhi).copy_(torch.cat(parts, 0))
+            eng.score_topk(peer.share_rows(qlo, qhi), g, k, out=peer.lists_out())
+            res = eng.merge_topk(*peer.share_lists())
+            for dst, src in zip(out_h, res):
+                dst.copy_(src, non_blocking=True)
+        elif world > 1:
             q = torch.cat(parts, 0)
             if even:
                 q_all = torch.empty((Q, 256), dtype=torch.float32, device=dev)
@@ -422,7 +444,10 @@ def run_ours(args):
                        "launch": ("one CUDA graph replay per step" if graph is not None else
                                   "three CUDA graph replays + four eager NCCL all-gathers per step" if seg is not None
                                   else "eager launches"),
-                       "parallelism": f"gallery sharded x{world}, queries replicated" if world > 1 else "single GPU"},
+                       "parallelism": (f"gallery sharded x{world}, queries replicated; exchange: " +
+                                       ("P2P writes into symmetric memory + device-side barriers (NVLink)"
+                                        if peer is not None else "NCCL all-gathers" + peer_note))
+                                      if world > 1 else "single GPU"},
             "queries_per_sec": Q / (ms * 1e-3),
             "e2e": {"value": Q * G / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "queries_per_sec": Q / (ms_e2e * 1e-3)},

@@ -136,8 +136,16 @@ class SeamEngine:
         self._weight_refs = (lw, lb)
 
     # ------------------------------------------------------------------ (a) aggregation
+    def _out(self, out: Optional[torch.Tensor], shape, dtype, name: str) -> torch.Tensor:
+        """A caller-provided output (e.g. a slice of a peer-shared buffer) or a fresh tensor."""
+        if out is None:
+            return torch.empty(shape, dtype=dtype, device=self.device)
+        if tuple(out.shape) != tuple(shape) or out.dtype != dtype or out.device != self.device or not out.is_contiguous():
+            raise ValueError(f"{name}: out must be a contiguous {tuple(shape)} {dtype} tensor on {self.device}")
+        return out
+
     def aggregate(self, seq: torch.Tensor, mask: Optional[torch.Tensor] = None,
-                  lens: Optional[torch.Tensor] = None, getatt: bool = False):
+                  lens: Optional[torch.Tensor] = None, getatt: bool = False, out: Optional[torch.Tensor] = None):
         """x3_1b (and attention weights) from the padded time-major track tensor.
 
         seq (1+Tmax, Q, 256) fp32 with dummy row 0, mask (Q, 1+Tmax) bool (True = padding):
@@ -160,7 +168,7 @@ class SeamEngine:
         l32 = None
         if lens is not None:
             l32 = lens.to(device=self.device, dtype=torch.int32).contiguous()
-        out = torch.empty((Q, D_MODEL), dtype=torch.float32, device=self.device)
+        out = self._out(out, (Q, D_MODEL), torch.float32, "aggregate")
         att = torch.empty((Q, Tmax), dtype=torch.float32, device=self.device) if getatt else None
         nbytes = int(self._lib.seam_aggregate_workspace_bytes(Q))
         ws = self._workspace("agg", nbytes)
@@ -198,16 +206,18 @@ class SeamEngine:
         return PreparedGallery(g=g, g16=g16, cg=cg, gstat=gstat, index_offset=index_offset)
 
     def score_topk(self, q: torch.Tensor, gallery: PreparedGallery, k: int,
-                   return_stats: bool = False):
-        """Best k gallery items per query: (scores (Q,k), margins (Q,k), idx (Q,k) int32)."""
+                   return_stats: bool = False, out=None):
+        """Best k gallery items per query: (scores (Q,k), margins (Q,k), idx (Q,k) int32).
+        ``out``: optional (scores, margins, idx) tensors to write into."""
         if q.dim() != 2 or q.shape[1] != D_MODEL:
             raise ValueError(f"queries must be (Q,256), got {tuple(q.shape)}")
         q = self._f32(q, "queries")
         Q, G = q.shape[0], gallery.G
         k = int(k)
-        sc = torch.empty((Q, k), dtype=torch.float32, device=self.device)
-        mg = torch.empty((Q, k), dtype=torch.float32, device=self.device)
-        ix = torch.empty((Q, k), dtype=torch.int32, device=self.device)
+        o = out if out is not None else (None, None, None)
+        sc = self._out(o[0], (Q, k), torch.float32, "score_topk scores")
+        mg = self._out(o[1], (Q, k), torch.float32, "score_topk margins")
+        ix = self._out(o[2], (Q, k), torch.int32, "score_topk idx")
         stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
         nbytes = int(self._lib.seam_score_workspace_bytes(self._h, Q, G, k))
         ws = self._workspace("score", nbytes)
