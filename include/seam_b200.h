@@ -172,7 +172,8 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
 
 /* Merge N per-shard top-k lists (after the all-gather) into one: lists are (N,Q,k)
  * contiguous; entries with idx < 0 are invalid.  Same ordering contract as seam_score_topk.
- * No reference counterpart (the reference ranks a single gallery). */
+ * No reference counterpart (the reference ranks a single gallery).  scores may be NULL: the score is
+ * softmax(0, margin)[1], recomputed bit-identically, so shards need only exchange margins and indices. */
 int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, const int32_t* idx, int N, int Q,
                     int k, float* out_score, float* out_margin, int32_t* out_idx, void* stream);
 

@@ -46,8 +46,8 @@ if peer is not None:
     for _ in range(3): gph.replay()
     torch.cuda.synchronize()
     if rank == 0:
-        same2 = torch.equal(ix2, ix1[:Qp]) and torch.equal(mg2, mg1[:Qp])
-        same3 = torch.equal(ix3, ix1[:Qp]) and torch.equal(mg3, mg1[:Qp])
+        same2 = torch.equal(ix2, ix1[:Qp]) and torch.equal(mg2, mg1[:Qp]) and torch.equal(sc2, sc1[:Qp])
+        same3 = torch.equal(ix3, ix1[:Qp]) and torch.equal(mg3, mg1[:Qp]) and torch.equal(sc3, sc1[:Qp])
         print(f"world={world}: peer-memory exchange vs single-GPU: eager identical={same2}, graph replay identical={same3}")
         ok = ok and same2 and same3
 flag = torch.tensor([1 if ok else 0], device=dev)

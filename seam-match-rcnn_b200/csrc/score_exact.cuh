@@ -763,7 +763,9 @@ __global__ void __launch_bounds__(256) rank_resolve_kernel(const RankResolvePara
 }
 
 // ---------------------------------------------------------------- shard merge
-// warp per query; each input list is sorted best first with idx < 0 marking padding.
+// warp per query; each input list is sorted best first with idx < 0 marking padding.  scores may be
+// null: the score is a function of the margin alone (softmax1(0, d), exactly what the re-score kernel
+// writes), so shards need not exchange it.
 __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ scores,
                                                          const float* __restrict__ margins,
                                                          const int32_t* __restrict__ idx, int N, int Q, int k,
@@ -780,7 +782,7 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict
     if (n == 0) {
       if (lane < k && idx[base + lane] >= 0) {
         d = margins[base + lane];
-        s = scores[base + lane];
+        s = scores ? scores[base + lane] : 0.f;
         id = idx[base + lane];
       }
     } else {
@@ -789,7 +791,7 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict
       int oi = INT_MAX;
       if (e < k && idx[base + e] >= 0) {
         od = margins[base + e];
-        os = scores[base + e];
+        os = scores ? scores[base + e] : 0.f;
         oi = idx[base + e];
       }
       if (wsort::ranks_before(od, oi, d, id)) {
@@ -803,7 +805,7 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict
   if (lane < k) {
     const size_t o = (size_t)qi * k + lane;
     const bool ok = id != INT_MAX;
-    out_score[o] = ok ? s : 0.f;
+    out_score[o] = ok ? (scores ? s : softmax1(0.f, d)) : 0.f;
     out_margin[o] = ok ? d : -INFINITY;
     out_idx[o] = ok ? id : -1;
   }

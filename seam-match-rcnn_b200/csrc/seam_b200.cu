@@ -894,7 +894,7 @@ int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, c
   if (N < 1 || Q < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_merge_topk: bad size");
   if (k < 1 || k > SEAM_MAX_K) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_merge_topk: k=%d outside [1,%d]", k, SEAM_MAX_K);
   if (Q == 0) return SEAM_OK;
-  if (!scores || !margins || !idx || !out_score || !out_margin || !out_idx)
+  if (!margins || !idx || !out_score || !out_margin || !out_idx)    // scores may be null: recomputed from the margins
     return fail(h, SEAM_ERR_BAD_ARG, "seam_merge_topk: null pointer");
   DeviceGuard guard(h->device);
   exact::merge_topk_kernel<<<(Q + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(

@@ -292,15 +292,16 @@ class SeamEngine:
                                                  self._stream()))
         return out
 
-    def merge_topk(self, scores: torch.Tensor, margins: torch.Tensor, idx: torch.Tensor):
-        """Merge (N,Q,k) per-shard lists into (Q,k)."""
-        N, Q, k = scores.shape
-        scores, margins = self._f32(scores, "scores"), self._f32(margins, "margins")
+    def merge_topk(self, scores: Optional[torch.Tensor], margins: torch.Tensor, idx: torch.Tensor):
+        """Merge (N,Q,k) per-shard lists into (Q,k); ``scores`` may be None (recomputed from the margins)."""
+        N, Q, k = margins.shape
+        margins = self._f32(margins, "margins")
+        scores = self._f32(scores, "scores") if scores is not None else None     # None: recomputed from the margins
         idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
         sc = torch.empty((Q, k), dtype=torch.float32, device=self.device)
         mg = torch.empty((Q, k), dtype=torch.float32, device=self.device)
         ix = torch.empty((Q, k), dtype=torch.int32, device=self.device)
-        self._check(self._lib.seam_merge_topk(self._h, scores.data_ptr(), margins.data_ptr(), idx.data_ptr(),
+        self._check(self._lib.seam_merge_topk(self._h, _ptr(scores), margins.data_ptr(), idx.data_ptr(),
                                               N, Q, k, sc.data_ptr(), mg.data_ptr(), ix.data_ptr(),
                                               self._stream()))
         return sc, mg, ix

@@ -203,7 +203,8 @@ class PeerExchange:
     over NVLink / NVSwitch) and a device-side barrier on the symmetric signal pads orders them.  Every
     operation is an ordinary stream operation, so the whole N-GPU step replays as ONE graph.
 
-    Buffers: ``q_all (Q,256)`` fp32 and ``lists (3,N,Q,k)`` (scores, margins, indices bit-cast to fp32);
+    Buffers: ``q_all (Q,256)`` fp32 and ``lists (2,N,Q,k)`` (margins, indices bit-cast to fp32; the scores
+    are a function of the margins and are recomputed by the merge);
     the kernels write their results straight into this rank's slices of the local buffers
     (``rows_out`` / ``lists_out``), from where they are copied to the peers.
     Raises at construction if symmetric memory is unavailable; callers then keep the NCCL path."""
@@ -217,12 +218,13 @@ class PeerExchange:
         self.Q, self.k = int(Q), int(k)
         dev = engine.device
         self._q = symm.empty((self.Q, 256), dtype=torch.float32, device=dev)
-        self._l = symm.empty((3, self.world, self.Q, self.k), dtype=torch.float32, device=dev)
+        self._l = symm.empty((2, self.world, self.Q, self.k), dtype=torch.float32, device=dev)
+        self._scores = torch.empty((self.Q, self.k), dtype=torch.float32, device=dev)   # local only
         self._hq = symm.rendezvous(self._q, self.group)
         self._hl = symm.rendezvous(self._l, self.group)
         others = [(self.rank + r) % self.world for r in range(1, self.world)]
         self._q_peers = [self._hq.get_buffer(r, (self.Q, 256), torch.float32) for r in others]
-        self._l_peers = [self._hl.get_buffer(r, (3, self.world, self.Q, self.k), torch.float32) for r in others]
+        self._l_peers = [self._hl.get_buffer(r, (2, self.world, self.Q, self.k), torch.float32) for r in others]
 
     def begin_step(self) -> None:
         """Nobody may overwrite a buffer a peer is still reading from the previous step."""
@@ -242,15 +244,15 @@ class PeerExchange:
     def lists_out(self):
         """Where this rank's (Q,k) scores, margins, idx are to be written."""
         mine = self._l[:, self.rank]
-        return mine[0], mine[1], mine[2].view(torch.int32)
+        return self._scores, mine[0], mine[1].view(torch.int32)
 
     def share_lists(self):
         """This rank's slot of the local list buffer -> the same slot on every peer; returns the gathered
-        (N,Q,k) scores, margins, idx -- contiguous views, ready for ``merge_topk``."""
+        (None, margins, idx) with (N,Q,k) contiguous views, ready for ``merge_topk``."""
         for buf in self._l_peers:
             buf[:, self.rank].copy_(self._l[:, self.rank], non_blocking=True)
         self._hl.barrier(channel=1)
-        return self._l[0], self._l[1], self._l[2].view(torch.int32)
+        return None, self._l[0], self._l[1].view(torch.int32)
 
 
 # ----------------------------------------------------------------------------------------
