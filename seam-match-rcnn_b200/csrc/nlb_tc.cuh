@@ -9,8 +9,10 @@
 //   M r ~= r_hi M_hi + r_hi M_lo + r_lo M_hi      (the dropped r_lo M_lo term is ~2^-22 relative)
 // is accumulated in fp32 in TMEM by tcgen05.mma kind::tf32.
 //
-// One CTA per 128 tracks, N = 256 output channels, K = 256 in 8 k-blocks of 32 fp32 (128-byte
-// swizzle).  Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
+// One CTA per 128 tracks, N = 256 output channels, K = 256 in 16 k-blocks of 16 fp32 (64-byte
+// swizzle) through a 4-stage ring of 48 KB.  Measured dead ends: fetching the CTA's pooled' tile into
+// shared memory by TMA (leaves room for 2 stages only: 30 us instead of 25), a 3-deep register
+// prefetch of pooled' started during the main loop (spills, competes with the operand loads: 33 us).  Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
 // warp 2 = TMEM allocator, warps 4..7 = epilogue (thread = track row).
 #pragma once
 #include <cstdint>
@@ -20,10 +22,10 @@
 namespace seam {
 namespace nlbtc {
 
-constexpr int BM = 128, BN = 256, BK = 32, NKB = 8, NSTAGE = 2;
+constexpr int BM = 128, BN = 256, BK = 16, NKB = 16, NSTAGE = 4;   // k-blocks of 16 fp32 = 64-byte swizzle rows
 constexpr int THREADS = 256;
-constexpr uint32_t A_BYTES = BM * BK * 4;   // 16 KB
-constexpr uint32_t B_BYTES = BN * BK * 4;   // 32 KB
+constexpr uint32_t A_BYTES = BM * BK * 4;   // 8 KB
+constexpr uint32_t B_BYTES = BN * BK * 4;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // r_hi, r_lo, M_hi, M_lo
 constexpr uint32_t OFF_BAR = NSTAGE * STAGE_BYTES;
 constexpr uint32_t OFF_TMEM = OFF_BAR + (2 * NSTAGE + 1) * 8;
@@ -98,10 +100,10 @@ nlb_tc_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ 
         const uint32_t st = ptx::smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t ah = ptx::umma_desc_k_sw128(st + k * 32);
-          const uint64_t al = ptx::umma_desc_k_sw128(st + A_BYTES + k * 32);
-          const uint64_t bh = ptx::umma_desc_k_sw128(st + 2 * A_BYTES + k * 32);
-          const uint64_t bl = ptx::umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES + k * 32);
+          const uint64_t ah = ptx::umma_desc_k_sw64(st + k * 32);
+          const uint64_t al = ptx::umma_desc_k_sw64(st + A_BYTES + k * 32);
+          const uint64_t bh = ptx::umma_desc_k_sw64(st + 2 * A_BYTES + k * 32);
+          const uint64_t bl = ptx::umma_desc_k_sw64(st + 2 * A_BYTES + B_BYTES + k * 32);
           ptx::umma_tf32(tmem_base, al, bh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
           ptx::umma_tf32(tmem_base, ah, bl, idesc, 1u);
           ptx::umma_tf32(tmem_base, ah, bh, idesc, 1u);

@@ -114,10 +114,10 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static int encode_map_f32_rows(seam_handle* h, CUtensorMap* map, const void* base, int rows, int box_rows) {
   const cuuint64_t dims[2] = {256, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {256 * 4};
-  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};   // 32 fp32 = one 128-byte swizzle row
+  const cuuint32_t box[2] = {(cuuint32_t)nlbtc::BK, (cuuint32_t)box_rows};   // 16 fp32 = one 64-byte swizzle row
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, SEAM_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
   return SEAM_OK;

@@ -158,6 +158,12 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
          (2ull << 61);
 }
+// Same for 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SWIZZLE_64B TMA box with a 64 B inner
+// extent); layout [61,64) = 4.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) |
+         (4ull << 61);
+}
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major.
 // fmt: 0 = fp16, 1 = bf16, 2 = tf32.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
