@@ -143,6 +143,13 @@ size_t seam_score_workspace_bytes(const seam_handle* h, int Q, int G, int k);
  * rowcnt (Q,P,4), rowbuf (Q,P,4,cap; base rounded up to a multiple of cap*8), counters,
  * fallback_rows} in the workspace, [13] workspace bytes. */
 int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out14);
+
+/* Pure host logic, callable without a device: the work decomposition of the scorer for num_sms persistent
+ * CTAs.  The (query tile, gallery tile) grid is linearised query-major; CTA b sweeps tiles
+ * [bounds[b], bounds[b+1]) (bounds_len >= CTAs + 1 entries), ranges balanced by cost (tiles + sample tiles
+ * + segment starts).  out6 = {query tiles, gallery tiles, CTAs, P, sub-list capacity, sample tiles per
+ * sampled segment}.  rank_variant != 0: the decomposition seam_rank_of_target_prepared uses. */
+int seam_score_partition(int num_sms, int Q, int G, int rank_variant, int32_t* bounds, int bounds_len, int32_t* out6);
 int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const void* g16, const float* cg,
                     const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin,
                     int32_t* out_idx, int32_t* stats, void* workspace, size_t workspace_bytes, void* stream);

@@ -91,6 +91,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_prepare_gallery.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     lib.seam_score_workspace_bytes.restype = sz
     lib.seam_score_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.seam_score_partition.restype = i32
+    lib.seam_score_partition.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int32), i32, C.POINTER(C.c_int32)]
     lib.seam_score_plan.restype = i32
     lib.seam_score_plan.argtypes = [vp, i32, i32, C.POINTER(C.c_int64)]
     lib.seam_score_topk.restype = i32

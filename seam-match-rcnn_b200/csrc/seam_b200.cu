@@ -486,7 +486,9 @@ static ScorePlan plan_score(int num_sms, int Q, int G, int nseed_override = -1) 
     return 0.0;
   };
   {
-    double lo = (double)total / s.grid, hi = (double)total / s.grid + 3.0 * (s.nseed + 1) + 2.0;
+    // every query tile starts a segment, every CTA boundary at most one more
+    const double all = (double)total + ((double)s.num_mtiles + s.grid) * (SEG_COST + s.nseed);
+    double lo = (double)total / s.grid, hi = 2.0 * all / s.grid + s.nseed + 2.0;
     for (int it = 0; it < 40; ++it) {
       const double mid = 0.5 * (lo + hi);
       if (walk(mid, s.tb) <= mid) hi = mid;
@@ -571,6 +573,21 @@ int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out) {
                          (int64_t)s.off_rq, (int64_t)s.off_anorm, (int64_t)s.off_thr, (int64_t)s.off_rowcnt,
                          (int64_t)s.off_rowbuf, (int64_t)s.off_cnt, (int64_t)s.off_rows, (int64_t)s.total};
   for (int i = 0; i < 14; ++i) out[i] = v[i];
+  return SEAM_OK;
+}
+
+// Pure host logic (no handle, no device): the tile ranges of the scorer's persistent CTAs.
+int seam_score_partition(int num_sms, int Q, int G, int rank_variant, int32_t* bounds, int bounds_len, int32_t* out6) {
+  if (num_sms < 1 || Q <= 0 || G <= 0 || !bounds || !out6) return SEAM_ERR_BAD_ARG;
+  const ScorePlan s = plan_score(num_sms, Q, G, rank_variant ? 0 : -1);
+  if (bounds_len < s.grid + 1) return SEAM_ERR_BAD_ARG;
+  for (int b = 0; b <= s.grid; ++b) bounds[b] = s.tb[b];
+  out6[0] = s.num_mtiles;
+  out6[1] = s.ntiles_n;
+  out6[2] = s.grid;
+  out6[3] = s.P;
+  out6[4] = s.CAP;
+  out6[5] = s.nseed;
   return SEAM_OK;
 }
 

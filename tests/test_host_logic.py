@@ -159,3 +159,58 @@ def test_sharded_search_gloo_world2(tmp_path, Q, G):
         s, d, i = torch.load(os.path.join(str(tmp_path), f"r{rank}.pt"))
         assert torch.equal(i[:, :kk].long(), i_ref) and (i[:, kk:] == -1).all()
         assert torch.allclose(d[:, :kk], d_ref, atol=1e-6) and torch.allclose(s[:, :kk], s_ref, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------
+# scorer work decomposition (pure host logic inside the C library: no device needed)
+# ----------------------------------------------------------------------------------------
+def _partition(num_sms, Q, G, rank_variant=0):
+    import ctypes as C
+    lib = pkg.load_library()
+    bounds = (C.c_int32 * (num_sms + 1))()
+    out = (C.c_int32 * 6)()
+    assert lib.seam_score_partition(num_sms, Q, G, rank_variant, bounds, num_sms + 1, out) == 0
+    mt, nt, grid, P, cap, nseed = list(out)
+    return list(bounds)[:grid + 1], mt, nt, grid, P, cap, nseed
+
+
+@pytest.mark.parametrize("Q,G", [(64, 1000), (15000, 15000), (10000, 50000), (10000, 6250), (10000, 125000),
+                                 (1, 1), (130, 257), (1000, 1000000), (200000, 300)])
+@pytest.mark.parametrize("rank_variant", [0, 1])
+def test_scorer_partition_is_a_balanced_cover(Q, G, rank_variant):
+    """CTA b sweeps tiles [tb[b], tb[b+1]): the ranges must tile the (query tile x gallery tile) grid
+    exactly, P must cover the CTAs that share any row, and the cost model (tiles + sample tiles of the
+    segments that hold a row's head or are swept first + a constant per segment) must be balanced."""
+    num_sms = 148
+    tb, mt, nt, grid, P, cap, nseed = _partition(num_sms, Q, G, rank_variant)
+    assert mt == -(-Q // 128) and nt == -(-G // 256)
+    total = mt * nt
+    assert grid == min(total, num_sms)
+    assert tb[0] == 0 and tb[-1] == total and all(a <= b for a, b in zip(tb, tb[1:]))
+    assert nseed == (0 if rank_variant else 4)
+    assert cap >= 128 and cap & (cap - 1) == 0
+    # pieces per row
+    first = {}
+    pieces = 1
+    for b in range(grid):
+        lo, hi = tb[b], tb[b + 1]
+        if lo == hi:
+            continue
+        for m in range(lo // nt, (hi - 1) // nt + 1):
+            first.setdefault(m, b)
+            pieces = max(pieces, b - first[m] + 1)
+    assert len(first) == mt and pieces <= P
+
+    def cost(lo, hi):
+        c, t, swept_first = 0.0, hi, True
+        while t > lo:                                   # segments, last first (score_tc.cuh: segment_before)
+            m = (t - 1) // nt
+            start = max(lo, m * nt)
+            n = t - start
+            c += 0.35 + n + (min(nseed, n) if (swept_first or start == m * nt) else 0)
+            swept_first, t = False, start
+        return c
+    costs = [cost(tb[b], tb[b + 1]) for b in range(grid) if tb[b + 1] > tb[b]]
+    if total >= 4 * num_sms:
+        # the last CTA takes the remainder (possibly less); nobody is far above the mean
+        assert max(costs) <= 1.15 * (sum(costs) / len(costs)) + 2.0
