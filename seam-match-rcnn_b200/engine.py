@@ -126,6 +126,7 @@ class SeamEngine:
         w = SeamWeights(**{f: tensors[f].data_ptr() for f in SeamWeights.FIELDS})
         self._check(self._lib.seam_load_weights(self._h, C.byref(w), self._stream()))
         self._weight_refs = tensors   # keep alive until the fold kernels have run
+        self.weights_epoch = getattr(self, "weights_epoch", 0) + 1
 
     def load_scorer(self, last_w: torch.Tensor, last_b: torch.Tensor) -> None:
         """Only ``last`` (e.g. ``match_predictor.last`` for the per-frame scorers)."""
@@ -134,6 +135,7 @@ class SeamEngine:
             raise ValueError("last.weight must be (2,256) and last.bias (2,)")
         self._check(self._lib.seam_load_scorer(self._h, lw.data_ptr(), lb.data_ptr(), self._stream()))
         self._weight_refs = (lw, lb)
+        self.weights_epoch = getattr(self, "weights_epoch", 0) + 1
 
     # ------------------------------------------------------------------ (a) aggregation
     def _out(self, out: Optional[torch.Tensor], shape, dtype, name: str) -> torch.Tensor:

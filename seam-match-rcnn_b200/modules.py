@@ -45,9 +45,12 @@ class _EngineMixin:
         state = self._hot_state()
         key = (tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in sorted(state.items())),
                self._extra_key())
-        if self.__dict__.get("_seam_key") != key:
+        # re-upload when the parameters changed -- or when somebody else loaded weights into this engine
+        # since (e.g. retrieval.evaluate_products switching to the per-frame scorer)
+        if self.__dict__.get("_seam_key") != key or self.__dict__.get("_seam_epoch") != getattr(eng, "weights_epoch", 0):
             self._upload(eng, state)
             self.__dict__["_seam_key"] = key
+            self.__dict__["_seam_epoch"] = getattr(eng, "weights_epoch", 0)
 
 
 class NONLocalBlock1D(nn.Module, _EngineMixin):

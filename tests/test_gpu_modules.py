@@ -208,4 +208,10 @@ def test_evaluate_products_rows(model, weights):
     assert torch.allclose(rep.perf, want, atol=1e-4)
     assert abs(rep.ret[2] - float((gr < 1).sum()) / P) < 1e-6
     assert rep.rank_median == float(torch.quantile(fr.float(), 0.5))
-    model._sync_weights(eng)                      # leave the shared engine with the module's own scorer
+    # somebody else's scorer in the module's engine must not leak into the module's next call
+    eng.load_scorer(fw, fb)
+    case = GOLDEN_CASES["t1"]
+    seq1, mask1, _, gal1 = case_inputs(case, weights)
+    _, idx1 = model.score_topk(seq1.to(DEV), mask1.to(DEV), gal1.to(DEV), k=5)
+    ref_q1, _ = so.aggregate_tracks(seq1, mask1, weights)
+    assert torch.equal(idx1.cpu(), so.rank_topk(so.pair_logits(ref_q1, gal1, weights), 5)[2])
