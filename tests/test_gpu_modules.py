@@ -215,3 +215,38 @@ def test_evaluate_products_rows(model, weights):
     _, idx1 = model.score_topk(seq1.to(DEV), mask1.to(DEV), gal1.to(DEV), k=5)
     ref_q1, _ = so.aggregate_tracks(seq1, mask1, weights)
     assert torch.equal(idx1.cpu(), so.rank_topk(so.pair_logits(ref_q1, gal1, weights), 5)[2])
+
+
+def test_evaluate_distance_fusions(model, weights):
+    """evaluate_movingfashion.py:294-316: ranks of the true shop item under the per-product average /
+    maximum of the frames' class-1 probabilities, against the same formulas in torch fp32 on the CPU."""
+    P, G = 23, 90
+    rs = np.random.RandomState(6)
+    lens = rs.randint(1, 6, size=P)
+    lens[5] = 0                                              # a product without tracked frames
+    frame_product = torch.tensor([p for p in range(P) for _ in range(int(lens[p]))])
+    perm = torch.from_numpy(rs.permutation(len(frame_product)))
+    frame_product = frame_product[perm]                      # frames arrive in any order
+    frame_desc = torch.from_numpy(rs.randn(len(frame_product), 256).astype(np.float32))
+    shop_desc = torch.from_numpy(rs.randn(G, 256).astype(np.float32))
+    target = torch.from_numpy(rs.permutation(G)[:P].astype(np.int64))
+    fw = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2, 256)).astype(np.float32))
+    fb = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2,)).astype(np.float32))
+    eng = model._engine_for(torch.device(DEV))
+    ranks, hits = pkg.evaluate_distance_fusions(eng, frame_desc, frame_product, shop_desc, target, (fw, fb),
+                                                max_pairs=7 * G)      # forces several chunks
+    wf = dict(weights)
+    wf["last.weight"], wf["last.bias"] = fw, fb
+    prob = so.match_scores(so.pair_logits(frame_desc, shop_desc, wf))
+    for p in range(P):
+        rows = (frame_product == p).nonzero().flatten()
+        if len(rows) == 0:
+            assert ranks[0, p] == G and ranks[1, p] == G
+            continue
+        for r, fused in enumerate((prob[rows].mean(0), prob[rows].max(0).values)):
+            t = int(target[p])
+            want = int(((fused > fused[t]) | ((fused == fused[t]) & (torch.arange(G) < t))).sum())
+            near = int(((fused - fused[t]).abs() <= 1e-6).sum())          # ties inside fp32 rounding may swap
+            assert abs(int(ranks[r, p]) - want) <= near, (p, r, int(ranks[r, p]), want)
+    assert hits.shape == (2, 4)
+    model._sync_weights(eng)
