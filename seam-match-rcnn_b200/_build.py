@@ -18,6 +18,10 @@ HEADERS = ["sm100_ptx.cuh", "warp_sort.cuh", "fold.cuh", "aggregate_warp.cuh", "
            "score_tc.cuh", "score_exact.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
+# SEAM_BUILD_DIAGNOSTICS=1 also compiles the scorer's measurement variants (partial epilogues, selected at
+# run time with SEAM_DEBUG_SCORE_MODE=1..5; they return wrong results and are not part of a product build)
+if os.environ.get("SEAM_BUILD_DIAGNOSTICS", "0") == "1":
+    NVCC_FLAGS = NVCC_FLAGS + ["-DSEAM_DIAGNOSTIC_VARIANTS"]
 
 
 def _nvcc() -> str:

@@ -172,10 +172,12 @@ int seam_create(seam_handle** out, int device) {
   // opt in to large dynamic shared memory once
   cudaFuncSetAttribute(score::score_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)score::SMEM_BYTES);
+#ifdef SEAM_DIAGNOSTIC_VARIANTS   // partial epilogues for measurements (wrong results): never in a product build
   cudaFuncSetAttribute(score::score_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(score::score_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(score::score_topk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(score::score_topk_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score::SMEM_BYTES);
+#endif
   cudaFuncSetAttribute(score::score_topk_kernel<score::VAR_RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)score::SMEM_BYTES);
   cudaFuncSetAttribute(aggw::aggregate_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -673,7 +675,11 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.CAP = s.CAP;
   sp.nseed = s.nseed;
   for (int b = 0; b <= s.grid; ++b) sp.tb[b] = s.tb[b];
-  sp.mode = env_int("SEAM_DEBUG_SCORE_MODE", 0);   // developer diagnostics only
+#ifdef SEAM_DIAGNOSTIC_VARIANTS
+  sp.mode = env_int("SEAM_DEBUG_SCORE_MODE", 0);   // developer diagnostics only (SEAM_BUILD_DIAGNOSTICS=1 builds)
+#else
+  sp.mode = 0;
+#endif
   sp.cg = cg;
   sp.thr_global = thr;
   sp.rowcnt = rowcnt;
@@ -689,11 +695,13 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
                   : nullptr;
   {
     ProfileScope prof(h, SEAM_KERNEL_SCORE, stream);
+#ifdef SEAM_DIAGNOSTIC_VARIANTS
     if (sp.mode == 2) score::score_topk_kernel<2><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     else if (sp.mode == 3) score::score_topk_kernel<3><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     else if (sp.mode == 4) score::score_topk_kernel<4><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     else if (sp.mode == 5) score::score_topk_kernel<5><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
-    else score::score_topk_kernel<0><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
+    else
+#endif score::score_topk_kernel<0><<<s.grid, score::THREADS, score::SMEM_BYTES, stream>>>(tmA, tmB, sp);
     SEAM_LAUNCHED(h, "score_topk_kernel");
   }
 
