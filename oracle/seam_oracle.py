@@ -326,6 +326,54 @@ def topk_hits(rank: int, k_thresholds=(1, 5, 10, 20)) -> List[int]:
     return [1 if rank < k else 0 for k in k_thresholds]
 
 
+def eval_product_loop(frame_desc: torch.Tensor, frame_product: torch.Tensor, shop_desc: torch.Tensor,
+                      target: torch.Tensor, w_frame: Weights, aggr_desc: torch.Tensor, shop_aggr: torch.Tensor,
+                      w_aggr: Weights, k_thresholds=(1, 5, 10, 20)):
+    """The per-product loop of the eval script, literally one product at a time, in fp32 (the reference
+    runs the frame-level parts in numpy fp16, evaluate_movingfashion.py:82-100).
+
+    For product p with frames F_p (``frame_product == p``) and true shop row t = target[p]:
+      * every frame on its own: ``compute_ranking`` :95-100, rank :216-222, hits ``k_accs`` :223-232;
+      * best frame of the product ("Product Max", ``k_accs_avg``) :233-241;
+      * average descriptor ``street_mat[best_inds].mean(0)`` :279-292 (``k_accs_avg_desc``);
+      * aggregated descriptor :252-277 (``k_accs_aggr_desc``), scored with the aggregator's ``last``;
+      * average / maximum of the frames' class-1 probabilities :294-316 (``k_accs_avg_dist``, ``k_accs_max_dist``).
+    Ranks are positions in the descending order with ties by lower index first (the reference's
+    ``argsort(...)[::-1]`` leaves ties unspecified).  Returns a dict of int64 tensors: ``frame_ranks (N,)``,
+    ``best``, ``avg_desc``, ``aggr``, ``avg_dist``, ``max_dist`` (each (P,), G for products without frames
+    except ``aggr``), and ``hits`` (6, len(k_thresholds)) in the order frame, best, avg_desc, aggr, avg_dist,
+    max_dist."""
+    P, G = int(target.shape[0]), int(shop_desc.shape[0])
+    col = torch.arange(G)
+
+    def rank_in(scores_1d: torch.Tensor, t: int) -> int:
+        return int(((scores_1d > scores_1d[t]) | ((scores_1d == scores_1d[t]) & (col < t))).sum())
+
+    out = {k: torch.full((P,), G, dtype=torch.int64) for k in ("best", "avg_desc", "aggr", "avg_dist", "max_dist")}
+    frame_ranks = torch.zeros(frame_desc.shape[0], dtype=torch.int64)
+    for p in range(P):
+        t = int(target[p])
+        d_aggr = logit_margin(pair_logits(aggr_desc[p:p + 1], shop_aggr, w_aggr))[0]
+        out["aggr"][p] = rank_in(d_aggr, t)
+        rows = (frame_product == p).nonzero().flatten()
+        if rows.numel() == 0:
+            continue
+        x5 = pair_logits(frame_desc[rows], shop_desc, w_frame)
+        d = logit_margin(x5)
+        for i, r in enumerate(rows.tolist()):
+            frame_ranks[r] = rank_in(d[i], t)
+        out["best"][p] = int(frame_ranks[rows].min())
+        avg = frame_desc[rows].mean(0, keepdim=True)
+        out["avg_desc"][p] = rank_in(logit_margin(pair_logits(avg, shop_desc, w_frame))[0], t)
+        prob = match_scores(x5)
+        out["avg_dist"][p] = rank_in(prob.mean(0), t)
+        out["max_dist"][p] = rank_in(prob.max(0).values, t)
+    rows_for_hits = [frame_ranks, out["best"], out["avg_desc"], out["aggr"], out["avg_dist"], out["max_dist"]]
+    out["hits"] = torch.tensor([[int((r < k).sum()) for k in k_thresholds] for r in rows_for_hits])
+    out["frame_ranks"] = frame_ranks
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # synthetic workloads (SURVEY.md section 8(d)); shared by tests and bench
 # --------------------------------------------------------------------------------------

@@ -126,3 +126,50 @@ def test_merge_topk_equals_global(weights):
     s, d, i = so.merge_topk(S, M, I, 20)
     s_ref, d_ref, i_ref = so.rank_topk(x5, 20)
     assert torch.equal(i, i_ref) and torch.equal(d, d_ref) and torch.equal(s, s_ref)
+
+
+def test_eval_product_loop_matches_the_numpy_formulas(weights):
+    """The fp32 restatement of the eval script's per-product loop against the script's own numpy
+    expressions (evaluate_movingfashion.py:94-106, 263-268, 279-316) evaluated in fp32/fp64: identical
+    ranks wherever the margins are not tied, and the hit counts that follow."""
+    rs = np.random.RandomState(21)
+    P, G = 9, 60
+    lens = [3, 1, 0, 4, 2, 5, 1, 2, 3]
+    frame_product = torch.tensor([p for p in range(P) for _ in range(lens[p])])
+    frame_desc = torch.from_numpy(rs.randn(len(frame_product), 256).astype(np.float32))
+    shop_desc = torch.from_numpy(rs.randn(G, 256).astype(np.float32))
+    shop_aggr = torch.from_numpy(rs.randn(G, 256).astype(np.float32))
+    aggr_desc = torch.from_numpy(rs.randn(P, 256).astype(np.float32))
+    target = torch.from_numpy(rs.permutation(G)[:P].astype(np.int64))
+    wf = dict(weights)
+    wf["last.weight"] = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2, 256)).astype(np.float32))
+    wf["last.bias"] = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2,)).astype(np.float32))
+    got = so.eval_product_loop(frame_desc, frame_product, shop_desc, target, wf, aggr_desc, shop_aggr, weights)
+
+    def np_scores(shop, street, w, b):                       # compute_distances, :101-106, in float64
+        sq = (shop[np.newaxis] - street[:, np.newaxis]) ** 2
+        raw = sq @ w.transpose() + b
+        e = np.exp(raw)
+        return (e / e.sum(2)[:, :, np.newaxis])[:, :, 1]
+
+    w64, b64 = wf["last.weight"].double().numpy(), wf["last.bias"].double().numpy()
+    aw, ab = weights["last.weight"].double().numpy(), weights["last.bias"].double().numpy()
+    shop64, saggr64 = shop_desc.double().numpy(), shop_aggr.double().numpy()
+    for p in range(P):
+        t = int(target[p])
+        rows = (frame_product == p).nonzero().flatten().numpy()
+        s_aggr = np_scores(saggr64, aggr_desc[p:p + 1].double().numpy(), aw, ab)[0]
+        assert int(got["aggr"][p]) == int((np.argsort(s_aggr)[::-1] == t).nonzero()[0][0])     # :268-269
+        if len(rows) == 0:
+            assert int(got["best"][p]) == G
+            continue
+        sc = np_scores(shop64, frame_desc[rows].double().numpy(), w64, b64)
+        ranks = [(np.argsort(sc[i])[::-1] == t).nonzero()[0][0] for i in range(len(rows))]   # :95-100, :216-222
+        assert got["frame_ranks"][rows].tolist() == [int(r) for r in ranks]
+        assert int(got["best"][p]) == int(min(ranks))
+        avg = frame_desc[rows].double().numpy().mean(0, keepdims=True)                         # :280
+        assert int(got["avg_desc"][p]) == int((np.argsort(np_scores(shop64, avg, w64, b64)[0])[::-1] == t).nonzero()[0][0])
+        assert int(got["avg_dist"][p]) == int((np.argsort(sc.mean(0))[::-1] == t).nonzero()[0][0])   # :296-298
+        assert int(got["max_dist"][p]) == int((np.argsort(sc.max(0))[::-1] == t).nonzero()[0][0])    # :307-309
+    assert got["hits"].shape == (6, 4)
+    assert got["hits"][0, 3] == int((got["frame_ranks"] < 20).sum())
