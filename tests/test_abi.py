@@ -62,3 +62,22 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "seam_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_ctypes_bindings_match_the_header():
+    """Every function declared in include/seam_b200.h is bound in _lib.py with as many arguments as the
+    header gives it (a drifted binding would pass garbage through the C ABI without any error)."""
+    import re
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "seam_b200.h")
+    with open(header) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    lib = pkg.load_library()
+    seen = 0
+    for m in re.finditer(r"\b(seam_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, f"{name} has no argtypes in _lib.py"
+        assert len(fn.argtypes) == n, f"{name}: header has {n} parameters, binding {len(fn.argtypes)}"
+        seen += 1
+    assert seen == len(pkg.declared_symbols())
