@@ -48,6 +48,12 @@ const char* seam_last_error(const seam_handle* h);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 uint64_t seam_launch_count(const seam_handle* h);
 
+/* Diagnostics.  Every blocking wait inside the kernels carries a wall-clock watchdog: instead of hanging
+ * the GPU, a protocol error traps the launch after leaving a record {tag, blockIdx.x, threadIdx.x, barrier
+ * shared address, parity, 0, 0, 0} in host-mapped memory.  Copies up to max_records records of 8 words into
+ * out and returns their number (0 in normal operation); works after the context has been lost. */
+int seam_watchdog_read(const seam_handle* h, uint32_t* out, int max_records);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, the library brackets each
  * of its named kernels with CUDA events on the launching stream.  seam_profile_read waits
  * for the recorded events of one kernel, returns their summed duration and count, and

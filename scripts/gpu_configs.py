@@ -8,7 +8,7 @@ from bench import random_init_weights
 dev = torch.device("cuda:0")
 e = pkg.SeamEngine(dev); e.load_weights(random_init_weights(dev))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-HBM, TF = 6541.5, 1639.0
+HBM, TF = 6542.1, 1632.4
 CFG = [("cfg1 64x10 vs 1,000", 64, 10, None, 1000),
        ("cfg2 15,000x10 vs 15,000", 15000, 10, None, 15000),
        ("cfg3 10,000x(2..4) vs 50,000", 10000, 4, (2, 4), 50000),
@@ -36,7 +36,7 @@ for name, Q, T, rag, G in CFG:
     pr = {k: v[0] / v[1] * 1e3 for k, v in e.profile_read().items() if v[1]}
     e.profile(False)
     agg_bytes = (nfr + Q) * 1024
-    msg = f"{name}: aggregate {pr['aggregate']:.1f} us = {agg_bytes / pr['aggregate'] / 1e3:.0f} GB/s ({agg_bytes / pr['aggregate'] / 1e3 / HBM * 100:.0f} %), nlb_gemm {pr['nlb_gemm']:.1f} us"
+    msg = f"{name}: aggregate {pr['aggregate']:.1f} us = {agg_bytes / pr['aggregate'] / 1e3:.0f} GB/s ({agg_bytes / pr['aggregate'] / 1e3 / HBM * 100:.0f} %)"
     if G:
         tfl = Q * G * 512 / pr['score'] / 1e6
         tot = sum(pr.values())

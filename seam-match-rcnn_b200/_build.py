@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libseam_b200.so")
 INFO_PATH = os.path.join(HERE, "libseam_b200.buildinfo")
 SOURCES = ["seam_b200.cu"]
-HEADERS = ["sm100_ptx.cuh", "warp_sort.cuh", "fold.cuh", "aggregate_warp.cuh", "aggregate_group.cuh", "nlb_gemm.cuh", "nlb_tc.cuh",
+HEADERS = ["sm100_ptx.cuh", "warp_sort.cuh", "fold.cuh", "aggregate_fused.cuh", "nlb_gemm.cuh",
            "score_tc.cuh", "score_exact.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -1,0 +1,865 @@
+// K1: temporal aggregation in ONE kernel -- streaming frame pass + the block's 256x256 map on the
+// tensor cores, nothing but the descriptors ever written to global memory.
+//
+// Replaces the per-track Python loop of TemporalAggregationNLB.forward's seq-branch,
+// models/match_head.py:133-154, and the block it calls, models/nlb.py:66-101, collapsed as in
+// DESIGN.md "K1 algebra":
+//   out = sum_t p_t x_t + M (sum_j q_j x_j) + (sum_j q_j) W_W b_g + b_W,   M = W_W W_g.
+//
+// Roles.  PRODUCER warps stream the tracks (bulk async copies into private shared-memory buffers,
+// frames pulled into registers once, four dots per frame, T x T interaction + softmax, both weighted
+// sums) exactly as a stand-alone streaming kernel would; instead of writing pooled' / r to global
+// memory they PUBLISH them into a batch of NB = 16 tracks in shared memory: r as two fp16 terms
+// (r * s = r1 + r2, s = a per-track power of two) in the 128-byte-swizzled K-major layout tcgen05 reads
+// as its B operand, pooled' in fp32.  Four HELPER warps own the tensor core: M * S = M1 + M2 (fp16
+// terms, fold.cuh) lives in TENSOR MEMORY for the whole kernel as the A operand (M1: 256 columns, the
+// first 224 k's of M2: 224 columns, accumulator: 32 columns = all 512; the last 32 k's of M2 sit in
+// 16 KB of shared memory), so a batch costs 96 small MMAs (D^T[256 ch x 16 tracks] = M1 r1 + M1 r2 +
+// M2 r1, fp32 accumulation: 22-bit operands, the dropped M2 r2 term is 2^-22 relative) and NO operand
+// traffic at all.  The helpers read the accumulator back (lane = channel, so every global store is a
+// 128-byte line), add pooled' and write the descriptor.  Batches are double-buffered: producers run up
+// to two batches ahead of the tensor core.
+//
+// Results do not depend on how tracks are grouped into batches (a column of D depends on its own track
+// only; the accumulation order over k is fixed), nor on which slot a track lands in.
+#pragma once
+#include <cstdint>
+#include <type_traits>
+#include <cuda_fp16.h>
+#include "fold.cuh"
+#include "sm100_ptx.cuh"
+
+namespace seam {
+namespace aggf {
+
+constexpr int D = 256;
+constexpr int NB = 16;                       // tracks per tensor-core batch (UMMA N)
+constexpr int HELPER_WARPS = 4;
+constexpr int KT = Fold::M2_KT;              // k's of M2 resident in tensor memory
+constexpr int KS = 256 - KT;                 // k's of M2 in shared memory (64-byte rows, SWIZZLE_64B)
+constexpr uint32_t COL_D = 0;                // accumulator: half h at COL_D + h*NB
+constexpr uint32_t COL_M1 = 32;              // M1 half h at COL_M1 + h*128 (k pair c at + c)
+constexpr uint32_t COL_M2 = COL_M1 + 256;    // M2 half h at COL_M2 + h*(KT/2)
+static_assert(COL_M2 + KT == 512 && 2 * NB <= (int)COL_M1 && KS == 32, "tensor-memory column map");
+
+constexpr uint32_t RT_TERM_BYTES = NB * 512;           // one fp16 term: 4 k-blocks x NB rows x 128 B
+constexpr uint32_t RT_BYTES = 2 * RT_TERM_BYTES;       // r1 | r2
+constexpr uint32_t TAIL_BYTES = 256 * KS * 2;          // 2 halves x 128 rows x 64 B
+constexpr uint32_t POOL_BYTES = NB * D * 4;
+constexpr uint32_t OFF_RT = 0;                         // [2] buffers
+constexpr uint32_t OFF_TAIL = OFF_RT + 2 * RT_BYTES;
+constexpr uint32_t OFF_META = OFF_TAIL + TAIL_BYTES;
+struct Meta {
+  int slot_track[2][NB];
+  float fscale[2][NB];
+  uint64_t tile_full[2];     // producers -> MMA      (NB x ARRIVALS arrivals)
+  uint64_t buf_free[2];      // helpers  -> producers (HELPER_WARPS arrivals)
+  uint64_t acc_full;         // MMA      -> helpers   (tcgen05.commit)
+  unsigned int next_slot;
+  uint32_t tmem_base;
+};
+constexpr uint32_t OFF_POOL = OFF_META + 512;          // [2] buffers, only when pooled' is staged in shared memory
+static_assert(sizeof(Meta) <= 512, "meta block");
+template <bool POOL_SMEM>
+__host__ __device__ constexpr uint32_t fused_bytes() {
+  return (OFF_POOL + (POOL_SMEM ? 2 * POOL_BYTES : 0) + 1023u) & ~1023u;
+}
+
+struct Params {
+  const float* seq;
+  const uint8_t* mask;     // (Q, 1+Tmax) or null
+  const int32_t* lens;     // (Q) or null
+  int Tmax, Q;
+  long long frame_stride, track_stride;   // floats
+  const float* fold;
+  float* out;      // (Q,256)
+  float* att;      // (Q,Tmax) or null
+};
+
+using ptx::treduce;
+
+// ---- packed fp32 pairs (FFMA2 / FMUL2): the streaming pass is bound by instruction issue
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+struct Vec8 {   // this lane's channels [4l,4l+4) and [128+4l,128+4l+4) as four pairs
+  u64 a, b, c, d;
+};
+__device__ __forceinline__ Vec8 load_vec8(const float* row, int lane) {
+  const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(row + 4 * lane);
+  const ulonglong2 hi = *reinterpret_cast<const ulonglong2*>(row + 128 + 4 * lane);
+  return Vec8{lo.x, lo.y, hi.x, hi.y};
+}
+__device__ __forceinline__ Vec8 zero_vec8() { return Vec8{0ull, 0ull, 0ull, 0ull}; }
+__device__ __forceinline__ float dot8(const Vec8& x, const Vec8& u) {
+  u64 acc = mul2(x.a, u.a);
+  acc = fma2(x.b, u.b, acc);
+  acc = fma2(x.c, u.c, acc);
+  acc = fma2(x.d, u.d, acc);
+  float lo, hi;
+  upk(acc, lo, hi);
+  return lo + hi;
+}
+__device__ __forceinline__ void fma8(Vec8& acc, u64 ss, const Vec8& x) {
+  acc.a = fma2(ss, x.a, acc.a);
+  acc.b = fma2(ss, x.b, acc.b);
+  acc.c = fma2(ss, x.c, acc.c);
+  acc.d = fma2(ss, x.d, acc.d);
+}
+__device__ __forceinline__ void unpack_vec8(const Vec8& v, float4& lo, float4& hi) {
+  upk(v.a, lo.x, lo.y);
+  upk(v.b, lo.z, lo.w);
+  upk(v.c, hi.x, hi.y);
+  upk(v.d, hi.z, hi.w);
+}
+
+// r * s = h1 + h2 in fp16 (h1 = round(r s), h2 = round(r s - h1): the residual is exact in fp32)
+__device__ __forceinline__ void split16(float a, float b, float s, uint32_t& t1, uint32_t& t2) {
+  const float as = a * s, bs = b * s;
+  const __half2 h1 = __floats2half2_rn(as, bs);
+  const float2 f1 = __half22float2(h1);
+  const __half2 h2 = __floats2half2_rn(as - f1.x, bs - f1.y);
+  t1 = *reinterpret_cast<const uint32_t*>(&h1);
+  t2 = *reinterpret_cast<const uint32_t*>(&h2);
+}
+// power of two s with max * s in [1,2) (1 for max == 0); *inv = 1 / s
+__device__ __forceinline__ float track_scale(float mx, float* inv) {
+  unsigned eb = (__float_as_uint(mx) >> 23) & 0xffu;
+  if (mx == 0.f) eb = 127u;
+  eb = eb < 1u ? 1u : (eb > 253u ? 253u : eb);
+  *inv = __uint_as_float(eb << 23);
+  return __uint_as_float((254u - eb) << 23);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Publishing a finished track into the current batch.  slot = running count of the CTA's finished
+// tracks; batch = slot / NB uses buffer batch & 1, which is free once the helpers are done with batch - 2.
+struct Slot {
+  int buf, pos;
+};
+__device__ __forceinline__ Slot claim_slot(Meta* meta, int lane) {
+  unsigned s = 0;
+  if (lane == 0) s = atomicAdd(&meta->next_slot, 1u);
+  s = __shfl_sync(ptx::FULL_MASK, s, 0);
+  const unsigned batch = s / NB;
+  Slot sl;
+  sl.buf = (int)(batch & 1u);
+  sl.pos = (int)(s % NB);
+  ptx::mbar_wait(&meta->buf_free[sl.buf], ((batch >> 1) & 1u) ^ 1u, 101);
+  return sl;
+}
+// 4 consecutive channels c..c+3 (c % 4 == 0) of both fp16 terms of row pos: one 8-byte store per term
+__device__ __forceinline__ void store_r4(uint8_t* rt, int pos, int c, const float4& r, float s) {
+  uint32_t a1, a2, b1, b2;
+  split16(r.x, r.y, s, a1, a2);
+  split16(r.z, r.w, s, b1, b2);
+  const uint32_t off = (uint32_t)(c >> 6) * (NB * 128) + (uint32_t)pos * 128 +
+                       ((((uint32_t)(c & 63) >> 3) ^ ((uint32_t)pos & 7u)) << 4) + ((uint32_t)(c & 7) << 1);
+  *reinterpret_cast<uint2*>(rt + off) = make_uint2(a1, b1);
+  *reinterpret_cast<uint2*>(rt + RT_TERM_BYTES + off) = make_uint2(a2, b2);
+}
+// 2 consecutive channels (c % 2 == 0)
+__device__ __forceinline__ void store_r2(uint8_t* rt, int pos, int c, float r0, float r1, float s) {
+  uint32_t a1, a2;
+  split16(r0, r1, s, a1, a2);
+  const uint32_t off = (uint32_t)(c >> 6) * (NB * 128) + (uint32_t)pos * 128 +
+                       ((((uint32_t)(c & 63) >> 3) ^ ((uint32_t)pos & 7u)) << 4) + ((uint32_t)(c & 7) << 1);
+  *reinterpret_cast<uint32_t*>(rt + off) = a1;
+  *reinterpret_cast<uint32_t*>(rt + RT_TERM_BYTES + off) = a2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Helper warps: tensor-memory set-up, one MMA batch per NB published tracks, read-back + store.
+//   units        producer units (warps or warp groups) of this CTA, unit u handles tracks
+//                first0 + u, first0 + u + stride, ...
+//   ARRIVALS     mbarrier arrivals per published track (warps per track)
+template <int ARRIVALS, bool POOL_SMEM>
+__device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw, int lane, int units, long long first0,
+                                            long long stride) {
+  Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
+  const uint32_t tmem = meta->tmem_base;
+  const uint32_t lane_base = tmem + ((uint32_t)(hw * 32) << 16);
+  const uint32_t* f32 = reinterpret_cast<const uint32_t*>(p.fold);
+  const int row = hw * 32 + lane;                        // row of a 128-row half this thread owns in tensor memory
+
+  // ---- M1, M2 -> tensor memory (coalesced reads of the pre-arranged images), M2's last k's -> shared memory
+  {
+    uint32_t v[32];
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __ldg(f32 + Fold::M1_IMG + (h * 128 + c0 + c) * 128 + row);
+        ptx::tmem_st_x32(lane_base + COL_M1 + h * 128 + c0, v);
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < KT / 2; c0 += 16) {
+        uint32_t w[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) w[c] = __ldg(f32 + Fold::M2_IMG + (h * (KT / 2) + c0 + c) * 128 + row);
+        ptx::tmem_st_x16(lane_base + COL_M2 + h * (KT / 2) + c0, w);
+      }
+    }
+    const uint4* tsrc = reinterpret_cast<const uint4*>(f32 + Fold::M2_TAIL);
+    uint4* tdst = reinterpret_cast<uint4*>(fz + OFF_TAIL);
+    for (int i = hw * 32 + lane; i < (int)(TAIL_BYTES / 16); i += HELPER_WARPS * 32) tdst[i] = __ldg(tsrc + i);
+    ptx::fence_proxy_async_smem();
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    ptx::named_bar_sync(1, HELPER_WARPS * 32);
+    ptx::tc_fence_after();
+  }
+
+  // tracks this CTA handles (static strided assignment of the producers)
+  long long n_cta = 0;
+  for (int u = 0; u < units; ++u) {
+    const long long f = first0 + u;
+    if (f < p.Q) n_cta += (p.Q - f + stride - 1) / stride;
+  }
+  const int nbatch = (int)((n_cta + NB - 1) / NB);
+  const float ms_inv = p.fold[Fold::CONSTS + 9];        // 1 / S
+  const uint32_t rt_addr = ptx::smem_u32(fz + OFF_RT), tail_addr = ptx::smem_u32(fz + OFF_TAIL);
+  constexpr uint32_t idesc = ptx::umma_idesc(0 /*fp16*/, 128, NB);
+
+#pragma unroll 1
+  for (int b = 0; b < nbatch; ++b) {
+    const int buf = b & 1;
+    const int cnt = (b == nbatch - 1) ? (int)(n_cta - (long long)b * NB) : NB;
+    if (hw == 0) {
+      // ------------------------------------------------ MMA issue (one lane)
+      if (lane == 0) {
+        for (int i = 0; i < (NB - cnt) * ARRIVALS; ++i) ptx::mbar_arrive(&meta->tile_full[buf]);   // slots nobody fills
+        ptx::mbar_wait(&meta->tile_full[buf], (uint32_t)(b >> 1) & 1u, 102);
+        ptx::tc_fence_after();
+        const uint32_t r1 = rt_addr + buf * RT_BYTES, r2 = r1 + RT_TERM_BYTES;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t d = tmem + COL_D + h * NB;
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {               // k-steps of 16
+            const uint32_t boff = (uint32_t)(ks >> 2) * (NB * 128) + (uint32_t)(ks & 3) * 32;
+            const uint64_t b1 = ptx::umma_desc_k_sw128(r1 + boff), b2 = ptx::umma_desc_k_sw128(r2 + boff);
+            const uint32_t a1 = tmem + COL_M1 + h * 128 + ks * 8;
+            ptx::umma_f16_ts(d, a1, b2, idesc, ks != 0 ? 1u : 0u);                                  // M1 r2 (small terms first)
+            if (ks * 16 < KT) {
+              ptx::umma_f16_ts(d, tmem + COL_M2 + h * (KT / 2) + ks * 8, b1, idesc, 1u);             // M2 r1
+            } else {
+              const uint64_t at = ptx::umma_desc_k_sw64(tail_addr + h * (128 * KS * 2) + (ks * 16 - KT) * 2);
+              ptx::umma_f16(d, at, b1, idesc, 1u);
+            }
+            ptx::umma_f16_ts(d, a1, b1, idesc, 1u);                                                 // M1 r1
+          }
+        }
+        ptx::umma_commit(&meta->acc_full);
+      }
+      __syncwarp();
+    }
+    // ---------------------------------------------------- read-back: thread = channel, register = track
+    ptx::mbar_wait(&meta->acc_full, (uint32_t)b & 1u, 103);
+    ptx::mbar_wait(&meta->tile_full[buf], (uint32_t)(b >> 1) & 1u, 104);   // acquire what the producers published (already complete)
+    ptx::tc_fence_after();
+    uint32_t d0[16], d1[16];
+    ptx::tmem_ld_x16(lane_base + COL_D, d0);
+    ptx::tmem_ld_x16(lane_base + COL_D + NB, d1);
+    ptx::tmem_ld_wait_x16(d0);
+    ptx::tmem_ld_wait_x16(d1);
+    ptx::tc_fence_before();
+    ptx::named_bar_sync(1, HELPER_WARPS * 32);           // the accumulator may be overwritten by the next batch
+    const int ch = hw * 32 + lane;
+    const float* pool = reinterpret_cast<const float*>(fz + OFF_POOL + buf * POOL_BYTES);
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      if (t < cnt) {                                      // warp-uniform
+        const int track = meta->slot_track[buf][t];
+        const float f = meta->fscale[buf][t] * ms_inv;
+        float* o = p.out + (size_t)track * D + ch;
+        float p0, p1;
+        if constexpr (POOL_SMEM) {
+          p0 = pool[t * D + ch];
+          p1 = pool[t * D + 128 + ch];
+        } else {
+          p0 = __ldcg(o);
+          p1 = __ldcg(o + 128);
+        }
+        o[0] = fmaf(f, __uint_as_float(d0[t]), p0);
+        o[128] = fmaf(f, __uint_as_float(d1[t]), p1);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&meta->buf_free[buf]);
+  }
+}
+
+// one-time CTA set-up shared by both kernels: barriers, slot counter, tensor-memory allocation
+template <int ARRIVALS>
+__device__ __forceinline__ void fused_setup(uint8_t* fz, int warp, int helper0) {
+  Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&meta->tile_full[i], NB * ARRIVALS);
+      ptx::mbar_init(&meta->buf_free[i], HELPER_WARPS);
+    }
+    ptx::mbar_init(&meta->acc_full, 1);
+    meta->next_slot = 0u;
+    ptx::fence_mbar_init();
+  }
+  if (warp == helper0) {
+    ptx::tmem_alloc(&meta->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+}
+__device__ __forceinline__ void fused_teardown(uint8_t* fz, int warp, int helper0) {
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == helper0) ptx::tmem_dealloc(reinterpret_cast<Meta*>(fz + OFF_META)->tmem_base, 512);
+}
+
+// ================================================================================================
+// Short tracks (up to TR = 4 / 10 / 16 frames): one producer WARP per track.
+// ================================================================================================
+template <int TR>
+struct Cfg;
+template <>
+struct Cfg<4> { static constexpr int NW = 16, SLOTS = 2, REGS_P = 104, REGS_H = 56; };   // the pool holds what the helpers release
+template <>
+struct Cfg<10> { static constexpr int NW = 12, SLOTS = 1, REGS_P = 152, REGS_H = 56; };
+template <>
+struct Cfg<16> { static constexpr int NW = 8, SLOTS = 1, REGS_P = 224, REGS_H = 56; };
+
+template <int TR>
+constexpr size_t warp_smem_bytes() {
+  return 1024 + fused_bytes<true>() + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * TR * D * 4   // track buffers
+         + (size_t)Cfg<TR>::NW * 64 * 4                                                   // per-warp scalars
+         + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * 8                                       // mbarriers
+         + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * 4;                                      // track lengths
+}
+template <int TR>
+constexpr int warp_threads() { return (Cfg<TR>::NW + HELPER_WARPS) * 32; }
+
+template <int TR>
+__global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregate_fused_warp_kernel(const Params p) {
+  constexpr int NW = Cfg<TR>::NW, SLOTS = Cfg<TR>::SLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* fz = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);        // fused area (1 KB aligned), then producers
+  uint8_t* pz = fz + fused_bytes<true>();
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(ptx::FULL_MASK, threadIdx.x >> 5, 0);
+  Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
+
+  const long long stride = (long long)gridDim.x * NW;
+  const long long first0 = (long long)blockIdx.x * NW;
+
+  float* xbuf = reinterpret_cast<float*>(pz) + (size_t)(warp < NW ? warp : 0) * SLOTS * TR * D;
+  float* scal = reinterpret_cast<float*>(pz) + (size_t)NW * SLOTS * TR * D + (warp < NW ? warp : 0) * 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pz + (size_t)NW * SLOTS * TR * D * 4 + (size_t)NW * 64 * 4) +
+                   (warp < NW ? warp : 0) * SLOTS;
+  int* slot_len = reinterpret_cast<int*>(pz + (size_t)NW * SLOTS * TR * D * 4 + (size_t)NW * 64 * 4 +
+                                         (size_t)NW * SLOTS * 8) + (warp < NW ? warp : 0) * SLOTS;
+  if (warp < NW && lane == 0) {
+    for (int i = 0; i < SLOTS; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_mbar_init();
+  }
+  fused_setup<1>(fz, warp, NW);
+
+  if (warp >= NW) {
+    ptx::reg_dec<Cfg<TR>::REGS_H>();
+    helper_role<1, true>(p, fz, warp - NW, lane, NW, first0, stride);
+  } else {
+    ptx::reg_inc<Cfg<TR>::REGS_P>();
+    const int Tmax = p.Tmax;
+    const long long first = first0 + warp;
+    const uint64_t pol = ptx::policy_evict_first();       // frames are read exactly once
+
+    // A track's length comes from lens[] or from its mask row.  peek() only issues that (dependent) load --
+    // one track ahead of its use -- and issue() turns the loaded word into the length and starts the copies.
+    auto peek = [&](long long track) -> int {
+      if (track >= p.Q) return 0;
+      if (p.lens) return p.lens[track];
+      if (p.mask) return lane <= Tmax ? (int)p.mask[(size_t)track * (1 + Tmax) + lane] : 0;
+      return 0;
+    };
+    auto issue = [&](long long track, int slot, int raw) {
+      int len = 0;
+      if (track < p.Q) {
+        if (p.lens) {
+          len = raw;
+        } else if (p.mask) {
+          // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
+          const uint32_t b = __ballot_sync(ptx::FULL_MASK, raw != 0);
+          const int end = b ? __ffs(b) - 1 : 1 + Tmax;
+          len = end - 1;
+        } else {
+          len = Tmax;
+        }
+        len = max(0, min(len, Tmax));
+      }
+      if (lane == 0) {
+        slot_len[slot] = len;
+        if (len > 0) ptx::mbar_arrive_expect_tx(&bars[slot], (uint32_t)len * (D * 4));
+        else ptx::mbar_arrive(&bars[slot]);
+      }
+      __syncwarp();
+      if (lane < len) {
+        const float* src = p.seq + (long long)(lane + 1) * p.frame_stride + track * p.track_stride;
+        ptx::bulk_load_1d_hint(xbuf + ((size_t)slot * TR + lane) * D, src, D * 4, &bars[slot], pol);
+      }
+    };
+
+    constexpr int AHEAD = SLOTS == 1 ? 1 : SLOTS - 1;     // tracks in flight ahead of the one being processed
+#pragma unroll 1
+    for (int i = 0; i < AHEAD; ++i) issue(first + i * stride, i, peek(first + i * stride));
+    int raw_next = peek(first + (long long)AHEAD * stride);
+
+    const float* fold = p.fold;
+    const Vec8 ut = load_vec8(fold + Fold::U_THETA, lane);
+    const Vec8 up = load_vec8(fold + Fold::U_PHI, lane);
+    const Vec8 ug = load_vec8(fold + Fold::U_G, lane);
+    const Vec8 wa = load_vec8(fold + Fold::W_A, lane);
+    const float c_s = fold[Fold::CONSTS + 3];
+    // scalar layout per frame: [a, d, b, c]; constants c_theta, 0, c_phi, c_g
+    const int comp = lane & 3;
+    const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
+                         : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
+
+    int it = 0;
+#pragma unroll 1
+    for (long long track = first; track < p.Q; track += stride, ++it) {
+      const int slot = it % SLOTS;
+      const uint32_t phase = (uint32_t)(it / SLOTS) & 1u;
+      if constexpr (SLOTS > 1) {
+        __syncwarp();                                  // every lane is done with the slot being refilled
+        issue(track + (long long)(SLOTS - 1) * stride, (it + SLOTS - 1) % SLOTS, raw_next);
+        raw_next = peek(track + (long long)SLOTS * stride);
+      }
+      ptx::mbar_wait(&bars[slot], phase, 105);
+      const int len = slot_len[slot];
+      const float* xs = xbuf + (size_t)slot * TR * D;
+
+      // One body, two instantiations: tracks with all TR frames (the common case) run without
+      // per-frame guards and with unrolled T x T loops.
+      auto process = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        // ---- frames -> registers, four dots per frame; every 4 frames a transposing butterfly leaves
+        // the 16 totals (a, d, b, c of 4 frames) in lanes 0..15
+        Vec8 x[TR];
+#pragma unroll
+        for (int t0 = 0; t0 < TR; t0 += 4) {
+          const int nf = TR - t0 < 4 ? TR - t0 : 4;     // frames in this group (compile time after unrolling)
+          float acc[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u;
+            if (u < nf) {
+              if (FULL || t < len) x[t] = load_vec8(xs + t * D, lane);
+              else x[t] = zero_vec8();
+              acc[4 * u + 0] = dot8(x[t], ut);
+              acc[4 * u + 1] = dot8(x[t], wa);
+              acc[4 * u + 2] = dot8(x[t], up);
+              acc[4 * u + 3] = dot8(x[t], ug);
+            }
+          }
+          if (nf > 2) {
+            const float tot = treduce<16>(acc, lane);
+            if (lane < 4 * nf) scal[4 * t0 + lane] = tot + my_const;
+          } else {
+            float a8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a8[i] = acc[i];
+            const float tot = treduce<8>(a8, lane);
+            if (lane < 4 * nf) scal[4 * t0 + lane] = tot + my_const;
+          }
+        }
+        if constexpr (SLOTS == 1) {
+          __syncwarp();                                // all lanes hold their frames in registers
+          issue(track + stride, 0, raw_next);
+          raw_next = peek(track + 2 * stride);
+        }
+        __syncwarp();
+
+        // ---- attention over the track's frames (lane = frame)
+        const int L = FULL ? TR : len;
+        const bool valid = lane < L;
+        const float inv_len = FULL ? 1.f / (float)TR : (len > 0 ? 1.f / (float)len : 0.f);
+        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) sc = *reinterpret_cast<const float4*>(scal + 4 * lane);   // a, d, b, c of my frame
+        float sum = 0.f;
+        if (FULL ? TR > 1 : len > 1) {
+#pragma unroll
+          for (int j = 0; j < (FULL ? TR : len); ++j) {
+            const float2 bc = *reinterpret_cast<const float2*>(scal + 4 * j + 2);
+            sum = fmaf(fmaxf(sc.x + bc.x, 0.f) * inv_len, bc.y, sum);
+          }
+        }
+        const float s_t = valid ? sc.y + sum + c_s : -INFINITY;
+        const float m = ptx::warp_max(s_t);
+        const float e_t = valid ? expf(s_t - m) : 0.f;
+        const float z = ptx::warp_sum(e_t);
+        const float p_t = valid ? e_t / z : 0.f;
+        __syncwarp();                                    // all lanes have read b, c, d
+        if (lane < TR) {
+          scal[4 * lane + 1] = p_t;
+          scal[4 * lane + 2] = p_t;
+        }
+        __syncwarp();
+        float q_j = 0.f;
+        if ((FULL ? TR > 1 : len > 1) && valid) {
+#pragma unroll
+          for (int t = 0; t < (FULL ? TR : len); ++t) {
+            const float2 ap = *reinterpret_cast<const float2*>(scal + 4 * t);
+            q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
+          }
+        }
+        const float qsum = ptx::warp_sum(q_j);
+        __syncwarp();                                    // all lanes have read the a_t
+        if (lane < TR) *reinterpret_cast<float4*>(scal + 4 * lane) = make_float4(p_t, p_t, q_j, q_j);
+        if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
+        __syncwarp();
+
+        // ---- weighted sums over frames, 8 channels per lane
+        Vec8 pov = zero_vec8(), rv = zero_vec8();
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+          if (FULL || t < len) {
+            const ulonglong2 pq = *reinterpret_cast<const ulonglong2*>(scal + 4 * t);   // {p,p}, {q,q}
+            fma8(pov, pq.x, x[t]);
+            fma8(rv, pq.y, x[t]);
+          }
+        }
+        float4 po0, po1, r0, r1;
+        unpack_vec8(pov, po0, po1);
+        unpack_vec8(rv, r0, r1);
+        if (FULL ? TR > 1 : len > 1) {
+          const float4 wbg0 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 4 * lane);
+          const float4 wbg1 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 128 + 4 * lane);
+          const float4 bw0 = *reinterpret_cast<const float4*>(fold + Fold::BW + 4 * lane);
+          const float4 bw1 = *reinterpret_cast<const float4*>(fold + Fold::BW + 128 + 4 * lane);
+          po0.x += fmaf(qsum, wbg0.x, bw0.x);
+          po0.y += fmaf(qsum, wbg0.y, bw0.y);
+          po0.z += fmaf(qsum, wbg0.z, bw0.z);
+          po0.w += fmaf(qsum, wbg0.w, bw0.w);
+          po1.x += fmaf(qsum, wbg1.x, bw1.x);
+          po1.y += fmaf(qsum, wbg1.y, bw1.y);
+          po1.z += fmaf(qsum, wbg1.z, bw1.z);
+          po1.w += fmaf(qsum, wbg1.w, bw1.w);
+        }
+        // ---- publish: pooled' (fp32) and r (two fp16 terms) into the batch under construction
+        float mx = fmaxf(fmaxf(fmaxf(fabsf(r0.x), fabsf(r0.y)), fmaxf(fabsf(r0.z), fabsf(r0.w))),
+                         fmaxf(fmaxf(fabsf(r1.x), fabsf(r1.y)), fmaxf(fabsf(r1.z), fabsf(r1.w))));
+        mx = ptx::warp_max(mx);
+        float inv;
+        const float s = track_scale(mx, &inv);
+        const Slot sl = claim_slot(meta, lane);
+        uint8_t* rt = fz + OFF_RT + sl.buf * RT_BYTES;
+        store_r4(rt, sl.pos, 4 * lane, r0, s);
+        store_r4(rt, sl.pos, 128 + 4 * lane, r1, s);
+        float* pool = reinterpret_cast<float*>(fz + OFF_POOL + sl.buf * POOL_BYTES) + sl.pos * D;
+        *reinterpret_cast<float4*>(pool + 4 * lane) = po0;
+        *reinterpret_cast<float4*>(pool + 128 + 4 * lane) = po1;
+        if (lane == 0) {
+          meta->slot_track[sl.buf][sl.pos] = (int)track;
+          meta->fscale[sl.buf][sl.pos] = inv;
+        }
+        ptx::fence_proxy_async_smem();                   // the r rows are read by the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&meta->tile_full[sl.buf]);
+      };
+      if (len == TR) process(std::true_type{});
+      else process(std::false_type{});
+    }
+  }
+  fused_teardown(fz, warp, NW);
+}
+
+
+// ================================================================================================
+// Long tracks (17..64 frames): a GROUP of GW = 2 / 4 producer warps per track, 16 frames per warp.
+// What crosses the warps of a group goes through a few hundred bytes of shared memory and five
+// named barriers per track: the per-frame scalars (a, d, b, c), the softmax maximum and denominator,
+// the partial weighted sums.  pooled' goes to global memory (the descriptor row itself) and is picked
+// up again from L2 by the helpers: no room for a shared-memory copy next to 128 KB of frame buffers.
+// ================================================================================================
+constexpr int FB = 16;                 // frames per warp
+constexpr int GWARPS = 8;              // producer warps per CTA
+constexpr int GTHREADS = (GWARPS + HELPER_WARPS) * 32;
+constexpr int GREGS_P = 224, GREGS_H = 56;
+
+template <int GW>
+struct alignas(16) GroupSmem {
+  float scal[FB * GW][4];              // per frame: a, d -> p, b, c -> q
+  float part[GW][2 * D];               // per warp: partial pooled | partial r
+  float red_max[GW];
+  float red_sum[GW];
+  float red_q[GW];
+  float red_rmax[GW];
+  unsigned int slot;
+  float pad[3];
+};
+template <int GW>
+struct GSmem {
+  float x[GWARPS][FB][D];              // 8 x 16 KB
+  GroupSmem<GW> g[GWARPS / GW];
+  uint64_t bar[GWARPS];
+};
+template <int GW>
+constexpr size_t group_smem_bytes() { return 1024 + fused_bytes<false>() + sizeof(GSmem<GW>); }
+
+template <int GW>
+__global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(const Params p) {
+  constexpr int GROUPS_PER_CTA = GWARPS / GW;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* fz = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  GSmem<GW>& s = *reinterpret_cast<GSmem<GW>*>(fz + fused_bytes<false>());
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(ptx::FULL_MASK, threadIdx.x >> 5, 0);
+  Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
+  const long long stride = (long long)gridDim.x * GROUPS_PER_CTA;
+  const long long first0 = (long long)blockIdx.x * GROUPS_PER_CTA;
+
+  if (warp < GWARPS && lane == 0) {
+    ptx::mbar_init(&s.bar[warp], 1);
+    ptx::fence_mbar_init();
+  }
+  fused_setup<GW>(fz, warp, GWARPS);
+
+  if (warp >= GWARPS) {
+    ptx::reg_dec<GREGS_H>();
+    helper_role<GW, false>(p, fz, warp - GWARPS, lane, GROUPS_PER_CTA, first0, stride);
+  } else {
+    ptx::reg_inc<GREGS_P>();
+    const int grp = warp / GW, wg = warp % GW;
+    GroupSmem<GW>& gs = s.g[grp];
+    float* xs = &s.x[warp][0][0];
+    uint64_t* bar = &s.bar[warp];
+    const int Tmax = p.Tmax;
+    const uint32_t bar_id = 2 + grp;                     // named barrier 1 belongs to the helpers
+    const long long first = first0 + grp;
+    const uint64_t pol = ptx::policy_evict_first();
+
+    // length of a track (every warp of the group derives it on its own)
+    auto track_len = [&](long long track) -> int {
+      if (track >= p.Q) return 0;
+      int len;
+      if (p.lens) {
+        len = p.lens[track];
+      } else if (p.mask) {
+        // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
+        const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
+        const uint32_t b0 = __ballot_sync(ptx::FULL_MASK, lane <= Tmax && m[lane] != 0);
+        const uint32_t b1 = __ballot_sync(ptx::FULL_MASK, 32 + lane <= Tmax && m[min(32 + lane, Tmax)] != 0);
+        const uint32_t b2 = __ballot_sync(ptx::FULL_MASK, lane == 0 && Tmax >= 64 && m[min(64, Tmax)] != 0);
+        const int end = b0 ? __ffs(b0) - 1 : b1 ? 32 + __ffs(b1) - 1 : b2 ? 64 : 1 + Tmax;
+        len = end - 1;
+      } else {
+        len = Tmax;
+      }
+      return max(0, min(len, Tmax));
+    };
+    // start the copies of this warp's frame block of one track
+    auto issue = [&](long long track, int len) {
+      const int nw = max(0, min(len - FB * wg, FB));
+      if (lane == 0) {
+        if (nw > 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nw * (D * 4));
+        else ptx::mbar_arrive(bar);
+      }
+      __syncwarp();
+      if (lane < nw) {
+        const float* src = p.seq + (long long)(FB * wg + lane + 1) * p.frame_stride + track * p.track_stride;
+        ptx::bulk_load_1d_hint(xs + (size_t)lane * D, src, D * 4, bar, pol);
+      }
+    };
+
+    const float* fold = p.fold;
+    const Vec8 ut = load_vec8(fold + Fold::U_THETA, lane);
+    const Vec8 up = load_vec8(fold + Fold::U_PHI, lane);
+    const Vec8 ug = load_vec8(fold + Fold::U_G, lane);
+    const Vec8 wa = load_vec8(fold + Fold::W_A, lane);
+    const float c_s = fold[Fold::CONSTS + 3];
+    const int comp = lane & 3;
+    const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
+                         : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
+
+    int len = track_len(first);
+    issue(first, len);
+    int it = 0;
+#pragma unroll 1
+    for (long long track = first; track < p.Q; track += stride, ++it) {
+      ptx::mbar_wait(bar, (uint32_t)it & 1u, 106);
+      const int nw = max(0, min(len - FB * wg, FB));
+
+      // ---- my 16 frames -> registers, four dots per frame, totals of 4 frames per butterfly
+      Vec8 x[FB];
+#pragma unroll
+      for (int t0 = 0; t0 < FB; t0 += 4) {
+        float acc[16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u;
+          if (t < nw) x[t] = load_vec8(xs + t * D, lane);
+          else x[t] = zero_vec8();
+          acc[4 * u + 0] = dot8(x[t], ut);
+          acc[4 * u + 1] = dot8(x[t], wa);
+          acc[4 * u + 2] = dot8(x[t], up);
+          acc[4 * u + 3] = dot8(x[t], ug);
+        }
+        const float tot = treduce<16>(acc, lane);
+        if (lane < 16) gs.scal[FB * wg + t0 + (lane >> 2)][comp] = tot + my_const;
+      }
+      // the buffer is free again: fetch this warp's block of the group's next track
+      const int len_next = track_len(track + stride);
+      __syncwarp();
+      issue(track + stride, len_next);
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #1 all scalars of the track are visible
+
+      // ---- attention over the track's frames: lane = (frame f of my block, half of the j / t range)
+      const int f = lane & 15, half = lane >> 4;
+      const int F = FB * wg + f;
+      const bool valid = F < len;
+      const float inv_len = len > 0 ? 1.f / (float)len : 0.f;
+      float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) sc = *reinterpret_cast<const float4*>(&gs.scal[F][0]);   // a, d, b, c of my frame
+      float sum = 0.f;
+      if (len > 1) {
+        for (int j = half; j < len; j += 2) {
+          const float2 bc = *reinterpret_cast<const float2*>(&gs.scal[j][2]);
+          sum = fmaf(fmaxf(sc.x + bc.x, 0.f) * inv_len, bc.y, sum);
+        }
+      }
+      sum += __shfl_xor_sync(ptx::FULL_MASK, sum, 16);
+      const float s_t = valid ? sc.y + sum + c_s : -INFINITY;
+      const float m_w = ptx::warp_max(s_t);
+      if (lane == 0) gs.red_max[wg] = m_w;
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #2 (also: nobody reads b, c, d any more)
+      float m = gs.red_max[0];
+#pragma unroll
+      for (int w = 1; w < GW; ++w) m = fmaxf(m, gs.red_max[w]);
+      const float e_t = valid ? expf(s_t - m) : 0.f;
+      const float z_w = ptx::warp_sum(half == 0 ? e_t : 0.f);
+      if (lane == 0) gs.red_sum[wg] = z_w;
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #3
+      float z = gs.red_sum[0];
+#pragma unroll
+      for (int w = 1; w < GW; ++w) z += gs.red_sum[w];
+      const float p_t = valid ? e_t / z : 0.f;
+      if (half == 0) gs.scal[F][1] = p_t;
+      if (p.att && half == 0 && F < Tmax) p.att[(size_t)track * Tmax + F] = p_t;
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #4 all p_t are visible
+      float q_j = 0.f;
+      if (len > 1 && valid) {
+        for (int t = half; t < len; t += 2) {
+          const float2 ap = *reinterpret_cast<const float2*>(&gs.scal[t][0]);
+          q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
+        }
+      }
+      q_j += __shfl_xor_sync(ptx::FULL_MASK, q_j, 16);
+      const float qsum_w = ptx::warp_sum(half == 0 ? q_j : 0.f);
+
+      // ---- partial weighted sums over my frames, 8 channels per lane
+      Vec8 pov = zero_vec8(), rv = zero_vec8();
+#pragma unroll
+      for (int t = 0; t < FB; ++t) {
+        const float pt = __shfl_sync(ptx::FULL_MASK, p_t, t);
+        const float qt = __shfl_sync(ptx::FULL_MASK, q_j, t);
+        if (t < nw) {
+          fma8(pov, pk(pt, pt), x[t]);
+          fma8(rv, pk(qt, qt), x[t]);
+        }
+      }
+      float4 po0, po1, r0, r1;
+      unpack_vec8(pov, po0, po1);
+      unpack_vec8(rv, r0, r1);
+      {
+        float* pw = &gs.part[wg][0];
+        *reinterpret_cast<float4*>(pw + 4 * lane) = po0;
+        *reinterpret_cast<float4*>(pw + 128 + 4 * lane) = po1;
+        *reinterpret_cast<float4*>(pw + D + 4 * lane) = r0;
+        *reinterpret_cast<float4*>(pw + D + 128 + 4 * lane) = r1;
+        // the sum of the warps' partial maxima bounds max |r|: it fixes the track's fp16 scale
+        float pm = fmaxf(fmaxf(fmaxf(fabsf(r0.x), fabsf(r0.y)), fmaxf(fabsf(r0.z), fabsf(r0.w))),
+                         fmaxf(fmaxf(fabsf(r1.x), fabsf(r1.y)), fmaxf(fabsf(r1.z), fabsf(r1.w))));
+        pm = ptx::warp_max(pm);
+        if (lane == 0) {
+          gs.red_q[wg] = qsum_w;
+          gs.red_rmax[wg] = pm;
+          if (wg == 0) gs.slot = atomicAdd(&meta->next_slot, 1u);
+        }
+      }
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #5 partial sums, maxima and the slot are visible
+
+      // ---- warp w finishes channels [CW w, CW (w+1)), CW = 256 / GW, and publishes them
+      {
+        const unsigned slot = gs.slot;
+        const unsigned batch = slot / NB;
+        const int buf = (int)(batch & 1u), pos = (int)(slot % NB);
+        float rb = gs.red_rmax[0];
+#pragma unroll
+        for (int w = 1; w < GW; ++w) rb += gs.red_rmax[w];
+        float inv;
+        const float scale = track_scale(rb, &inv);
+        ptx::mbar_wait(&meta->buf_free[buf], ((batch >> 1) & 1u) ^ 1u, 107);
+        uint8_t* rt = fz + OFF_RT + buf * RT_BYTES;
+        constexpr int CW = D / GW;
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 64) {
+          const int c = CW * wg + c0 + 2 * lane;
+          float2 po = make_float2(0.f, 0.f), rr = po;
+#pragma unroll
+          for (int w = 0; w < GW; ++w) {
+            const float2 a = *reinterpret_cast<const float2*>(&gs.part[w][c]);
+            const float2 b = *reinterpret_cast<const float2*>(&gs.part[w][D + c]);
+            po.x += a.x;
+            po.y += a.y;
+            rr.x += b.x;
+            rr.y += b.y;
+          }
+          if (len > 1) {
+            float qsum = gs.red_q[0];
+#pragma unroll
+            for (int w = 1; w < GW; ++w) qsum += gs.red_q[w];
+            const float2 wbg = *reinterpret_cast<const float2*>(fold + Fold::WBG + c);
+            const float2 bw = *reinterpret_cast<const float2*>(fold + Fold::BW + c);
+            po.x += fmaf(qsum, wbg.x, bw.x);
+            po.y += fmaf(qsum, wbg.y, bw.y);
+          }
+          *reinterpret_cast<float2*>(p.out + (size_t)track * D + c) = po;
+          store_r2(rt, pos, c, rr.x, rr.y, scale);
+        }
+        if (wg == 0 && lane == 0) {
+          meta->slot_track[buf][pos] = (int)track;
+          meta->fscale[buf][pos] = inv;
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&meta->tile_full[buf]);
+      }
+      len = len_next;
+    }
+  }
+  fused_teardown(fz, warp, GWARPS);
+}
+
+}  // namespace aggf
+}  // namespace seam

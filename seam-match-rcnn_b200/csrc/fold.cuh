@@ -13,6 +13,7 @@
 // Sums are accumulated in fp64 and rounded once to fp32.
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 
 namespace seam {
 
@@ -28,9 +29,16 @@ struct Fold {
   static constexpr int DW = 1792;
   static constexpr int LAST_W = 2048;   // (2,256)
   static constexpr int MT = 2560;       // Mt[k*256 + o] = M[o][k], fp32
-  static constexpr int M_HI = MT + 65536;    // M[o*256 + k] tf32-truncated (row = output channel, K-major)
-  static constexpr int M_LO = M_HI + 65536;  // M - M_HI
-  static constexpr int TOTAL = M_LO + 65536;
+  // M as two fp16 terms, M * S = M1 + M2 (S = the power of two that brings max|M| into [1,2); CONSTS+8..10),
+  // laid out as the fused aggregation kernel wants them (aggregate_fused.cuh): images of the tensor-memory
+  // resident A operand -- word (h*COLS + c)*128 + lane = {M[128h+lane][2c], M[128h+lane][2c+1]} -- for all
+  // of M1 (COLS = 128) and the first M2_KT k's of M2 (COLS = M2_KT/2), and the remaining k's of M2 as the
+  // 64-byte-swizzled K-major shared-memory tile (128 rows x 64 B per half).
+  static constexpr int M2_KT = 224;
+  static constexpr int M1_IMG = MT + 65536;                  // 2*128*128 words
+  static constexpr int M2_IMG = M1_IMG + 2 * 128 * 128;      // 2*(M2_KT/2)*128 words
+  static constexpr int M2_TAIL = M2_IMG + M2_KT * 128;       // 256 rows x (256-M2_KT) fp16
+  static constexpr int TOTAL = M2_TAIL + 256 * (256 - M2_KT) / 2;
 };
 
 struct FoldIn {
@@ -92,6 +100,7 @@ __global__ void fold_vectors_kernel(FoldIn in, float* __restrict__ fold) {
     fold[Fold::CONSTS + 5] = in.last_b[0];
     fold[Fold::CONSTS + 6] = in.last_b[1];
     fold[Fold::CONSTS + 7] = 0.f;
+    fold[Fold::CONSTS + 8] = 0.f;   // max |M| (fold_matrix_kernel, atomicMax on the bit image)
   }
 }
 
@@ -120,9 +129,46 @@ __global__ void fold_matrix_kernel(const float* __restrict__ W_w, const float* _
   for (int c = 0; c < 128; ++c) s += (double)wrow[c] * (double)g_w[c * 256 + k];
   const float m = (float)s;
   fold[Fold::MT + k * 256 + o] = m;
-  const float hi = __uint_as_float(__float_as_uint(m) & 0xffffe000u);   // tf32 truncation
-  fold[Fold::M_HI + o * 256 + k] = hi;
-  fold[Fold::M_LO + o * 256 + k] = m - hi;
+  float amax = fabsf(m);
+  for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  if ((k & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(fold + Fold::CONSTS + 8), __float_as_uint(amax));
+}
+
+// power of two that brings a non-negative finite x into [1,2) (1 for x == 0); *inv = its reciprocal
+__device__ __forceinline__ float pow2_normaliser(float x, float* inv) {
+  unsigned eb = (__float_as_uint(x) >> 23) & 0xffu;
+  if (x == 0.f) eb = 127u;
+  eb = eb < 1u ? 1u : (eb > 253u ? 253u : eb);
+  *inv = __uint_as_float(eb << 23);
+  return __uint_as_float((254u - eb) << 23);
+}
+
+// after fold_matrix_kernel (same stream): the fp16 two-term images of M * S.  grid = 256 blocks (o), 256 threads (k)
+__global__ void fold_m16_kernel(float* __restrict__ fold) {
+  const int o = blockIdx.x, k = threadIdx.x;
+  float inv;
+  const float S = pow2_normaliser(fold[Fold::CONSTS + 8], &inv);
+  if (o == 0 && k == 0) {
+    fold[Fold::CONSTS + 9] = inv;   // 1 / S
+    fold[Fold::CONSTS + 10] = S;
+  }
+  const float m = fold[Fold::MT + k * 256 + o] * S;
+  const __half h1 = __float2half_rn(m);
+  const __half h2 = __float2half_rn(m - __half2float(h1));
+  const unsigned u1 = __half_as_ushort(h1), u2 = __half_as_ushort(h2);
+  const unsigned p1 = __shfl_down_sync(0xffffffffu, u1, 1), p2 = __shfl_down_sync(0xffffffffu, u2, 1);
+  if (k & 1) return;
+  unsigned* f = reinterpret_cast<unsigned*>(fold);
+  const int h = o >> 7, row = o & 127, c = k >> 1;
+  f[Fold::M1_IMG + (h * 128 + c) * 128 + row] = u1 | (p1 << 16);
+  if (k < Fold::M2_KT) {
+    f[Fold::M2_IMG + (h * (Fold::M2_KT / 2) + c) * 128 + row] = u2 | (p2 << 16);
+  } else {
+    constexpr int KS = 256 - Fold::M2_KT;            // 32 fp16 = 64-byte rows, SWIZZLE_64B: chunk ^= (row >> 1) & 3
+    const int kk = k - Fold::M2_KT;
+    const int byte = h * (128 * KS * 2) + row * (KS * 2) + (((kk >> 3) ^ ((row >> 1) & 3)) << 4) + (kk & 7) * 2;
+    f[Fold::M2_TAIL + (byte >> 2)] = u2 | (p2 << 16);
+  }
 }
 
 }  // namespace seam

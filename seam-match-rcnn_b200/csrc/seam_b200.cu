@@ -14,11 +14,9 @@
 #include <cuda_runtime.h>
 
 #include "../../include/seam_b200.h"
-#include "aggregate_warp.cuh"
-#include "aggregate_group.cuh"
+#include "aggregate_fused.cuh"
 #include "fold.cuh"
 #include "nlb_gemm.cuh"
-#include "nlb_tc.cuh"
 #include "score_exact.cuh"
 #include "score_tc.cuh"
 
@@ -37,6 +35,9 @@ struct seam_handle {
   PFN_encodeTiled encode = nullptr;
   uint64_t launches = 0;
   bool profiling = false;
+  unsigned int* watchdog = nullptr;   // host-mapped record buffer of the device-side wait watchdogs
+  // developer overrides, read once at seam_create (never consulted on the hot path)
+  int dbg_score_grid = 0, dbg_agg_grid = 0, dbg_cta_ns = 0, score_nseed = 4;
   struct Span { int kernel; cudaEvent_t a, b; };
   std::vector<Span> spans;            // recorded while profiling
   std::vector<cudaEvent_t> free_events;
@@ -70,6 +71,13 @@ struct ProfileScope {
 };
 
 static thread_local char g_create_err[256] = "";
+
+static unsigned int* g_watchdog_host[64] = {};
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
 
 static int fail(seam_handle* h, int code, const char* fmt, ...) {
   va_list ap;
@@ -111,24 +119,19 @@ struct DeviceGuard {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int encode_map_f32_rows(seam_handle* h, CUtensorMap* map, const void* base, int rows, int box_rows) {
-  const cuuint64_t dims[2] = {256, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {256 * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)nlbtc::BK, (cuuint32_t)box_rows};   // 16 fp32 = one 64-byte swizzle row
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(h, SEAM_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
-  return SEAM_OK;
-}
-
 template <int TR>
-static void launch_aggregate_warp(const aggw::Params& p, int num_sms, cudaStream_t stream) {
-  constexpr int NW = aggw::Cfg<TR>::NW;
+static void launch_aggregate_warp(const aggf::Params& p, int num_sms, cudaStream_t stream) {   // num_sms = CTA cap
+  constexpr int NW = aggf::Cfg<TR>::NW;
   const int want = (p.Q + NW - 1) / NW;
   const int grid = want < num_sms ? want : num_sms;
-  aggw::aggregate_warp_kernel<TR><<<grid, NW * 32, aggw::smem_bytes<TR>(), stream>>>(p);
+  aggf::aggregate_fused_warp_kernel<TR><<<grid, aggf::warp_threads<TR>(), aggf::warp_smem_bytes<TR>(), stream>>>(p);
+}
+template <int GW>
+static void launch_aggregate_group(const aggf::Params& p, int num_sms, cudaStream_t stream) {
+  constexpr int GPC = aggf::GWARPS / GW;
+  const int want = (p.Q + GPC - 1) / GPC;
+  const int grid = want < num_sms ? want : num_sms;
+  aggf::aggregate_fused_group_kernel<GW><<<grid, aggf::GTHREADS, aggf::group_smem_bytes<GW>(), stream>>>(p);
 }
 
 extern "C" {
@@ -169,6 +172,26 @@ int seam_create(seam_handle** out, int device) {
     return fail(nullptr, SEAM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  h->dbg_score_grid = env_int("SEAM_DEBUG_SCORE_GRID", 0);
+  h->dbg_agg_grid = env_int("SEAM_DEBUG_AGG_GRID", 0);
+  h->dbg_cta_ns = env_int("SEAM_DEBUG_CTA_NS", 0);
+  h->score_nseed = env_int("SEAM_SCORE_NSEED", 4);
+  // watchdog records live in host-mapped memory so that they survive a trapped launch: one buffer per
+  // device for the life of the process (the device-side pointer must never dangle)
+  if (device < 64) {
+    if (!g_watchdog_host[device]) {
+      unsigned int* hp = nullptr;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&hp), 1024, cudaHostAllocMapped) == cudaSuccess) {
+        memset(hp, 0, 1024);
+        unsigned int* dptr = nullptr;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), hp, 0) == cudaSuccess &&
+            cudaMemcpyToSymbol(ptx::g_watchdog, &dptr, sizeof(dptr)) == cudaSuccess)
+          g_watchdog_host[device] = hp;
+      }
+      cudaGetLastError();
+    }
+    h->watchdog = g_watchdog_host[device];
+  }
   // opt in to large dynamic shared memory once
   cudaFuncSetAttribute(score::score_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)score::SMEM_BYTES);
@@ -180,17 +203,16 @@ int seam_create(seam_handle** out, int device) {
 #endif
   cudaFuncSetAttribute(score::score_topk_kernel<score::VAR_RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)score::SMEM_BYTES);
-  cudaFuncSetAttribute(aggw::aggregate_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)aggw::smem_bytes<4>());
-  cudaFuncSetAttribute(aggw::aggregate_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)aggw::smem_bytes<10>());
-  cudaFuncSetAttribute(aggw::aggregate_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)aggw::smem_bytes<16>());
-  cudaFuncSetAttribute(aggg::aggregate_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)sizeof(aggg::Smem<2>));
-  cudaFuncSetAttribute(aggg::aggregate_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)sizeof(aggg::Smem<4>));
-  cudaFuncSetAttribute(nlbtc::nlb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nlbtc::SMEM_BYTES);
+  cudaFuncSetAttribute(aggf::aggregate_fused_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggf::warp_smem_bytes<4>());
+  cudaFuncSetAttribute(aggf::aggregate_fused_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggf::warp_smem_bytes<10>());
+  cudaFuncSetAttribute(aggf::aggregate_fused_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggf::warp_smem_bytes<16>());
+  cudaFuncSetAttribute(aggf::aggregate_fused_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggf::group_smem_bytes<2>());
+  cudaFuncSetAttribute(aggf::aggregate_fused_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)aggf::group_smem_bytes<4>());
   cudaFuncSetAttribute(nlbgemm::nlb_full_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)((SEAM_MAX_T * 257 + 2 * SEAM_MAX_T) * sizeof(float)));
   if ((e = cudaGetLastError()) != cudaSuccess) {
@@ -211,6 +233,16 @@ void seam_destroy(seam_handle* h) {
     cudaFree(h->fold);
   }
   delete h;
+}
+
+int seam_watchdog_read(const seam_handle* h, uint32_t* out, int max_records) {
+  if (!h || !h->watchdog || !out || max_records <= 0) return 0;
+  const volatile unsigned int* w = h->watchdog;
+  int n = (int)w[0];
+  if (n > ptx::WATCHDOG_RECORDS) n = ptx::WATCHDOG_RECORDS;
+  if (n > max_records) n = max_records;
+  for (int i = 0; i < n * 8; ++i) out[i] = w[8 + i];
+  return n;
 }
 
 const char* seam_last_error(const seam_handle* h) { return h ? h->err : g_create_err; }
@@ -259,6 +291,8 @@ int seam_load_weights(seam_handle* h, const seam_weights* w, void* stream_) {
   SEAM_LAUNCHED(h, "fold_vectors_kernel");
   fold_matrix_kernel<<<256, 256, 0, stream>>>(w->W_w, w->g_w, h->fold);
   SEAM_LAUNCHED(h, "fold_matrix_kernel");
+  fold_m16_kernel<<<256, 256, 0, stream>>>(h->fold);
+  SEAM_LAUNCHED(h, "fold_m16_kernel");
   h->have_scorer = h->have_aggregator = true;
   return SEAM_OK;
 }
@@ -275,13 +309,15 @@ int seam_load_scorer(seam_handle* h, const float* last_w, const float* last_b, v
 
 // ------------------------------------------------------------------------------ aggregation
 size_t seam_aggregate_workspace_bytes(int Q) {
-  if (Q <= 0) return 256;
-  return 3 * align_up((size_t)Q * 256 * 4, 256);   // pooled', r_hi, r_lo
+  (void)Q;
+  return 256;   // the fused kernel keeps every intermediate on the SM
 }
 
 int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const int32_t* lens, int Tmax, int Q,
                    int64_t frame_stride, int64_t track_stride, float* out, float* att, void* workspace,
                    size_t workspace_bytes, void* stream_) {
+  (void)workspace;
+  (void)workspace_bytes;
   if (!h) return SEAM_ERR_BAD_ARG;
   if (!h->have_aggregator) return fail(h, SEAM_ERR_STATE, "seam_aggregate: weights not loaded");
   if (Q < 0 || Tmax < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: negative size");
@@ -294,22 +330,12 @@ int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const 
     return SEAM_OK;
   }
   if (Tmax > SEAM_MAX_T) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: Tmax=%d exceeds %d", Tmax, SEAM_MAX_T);
-  if (!seq || !workspace) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: null pointer");
+  if (!seq) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: null pointer");
   if (!aligned16(seq) || !aligned16(out) || (frame_stride & 3) || (track_stride & 3))
     return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: seq/out must be 16-byte aligned, strides multiples of 4");
-  if ((reinterpret_cast<uintptr_t>(workspace) & 255u))
-    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: workspace must be 256-byte aligned");
-  if (workspace_bytes < seam_aggregate_workspace_bytes(Q))
-    return fail(h, SEAM_ERR_STATE, "seam_aggregate: workspace too small (%zu < %zu)", workspace_bytes,
-                seam_aggregate_workspace_bytes(Q));
-  const size_t plane = align_up((size_t)Q * 256 * 4, 256);
-  float* pooled = static_cast<float*>(workspace);
-  float* r_hi = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plane);
-  float* r_lo = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * plane);
-
   {
     ProfileScope prof(h, SEAM_KERNEL_AGGREGATE, stream);
-    aggw::Params p;
+    aggf::Params p;
     p.seq = seq;
     p.mask = mask;
     p.lens = lens;
@@ -318,41 +344,15 @@ int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const 
     p.frame_stride = frame_stride;
     p.track_stride = track_stride;
     p.fold = h->fold;
-    p.pooled = pooled;
-    p.r_hi = r_hi;
-    p.r_lo = r_lo;
+    p.out = out;
     p.att = att;
-    if (Tmax <= 4) launch_aggregate_warp<4>(p, h->num_sms, stream);
-    else if (Tmax <= 10) launch_aggregate_warp<10>(p, h->num_sms, stream);
-    else if (Tmax <= 16) launch_aggregate_warp<16>(p, h->num_sms, stream);
-    else if (Tmax <= 32) {   // two warps per track
-      const int want = (Q + 3) / 4;
-      aggg::aggregate_group_kernel<2><<<want < h->num_sms ? want : h->num_sms, aggg::THREADS, sizeof(aggg::Smem<2>),
-                                        stream>>>(p);
-    } else {                 // 33..64 frames: four warps per track
-      const int want = (Q + 1) / 2;
-      aggg::aggregate_group_kernel<4><<<want < h->num_sms ? want : h->num_sms, aggg::THREADS, sizeof(aggg::Smem<4>),
-                                        stream>>>(p);
-    }
+    const int cap = h->dbg_agg_grid > 0 && h->dbg_agg_grid < h->num_sms ? h->dbg_agg_grid : h->num_sms;
+    if (Tmax <= 4) launch_aggregate_warp<4>(p, cap, stream);
+    else if (Tmax <= 10) launch_aggregate_warp<10>(p, cap, stream);
+    else if (Tmax <= 16) launch_aggregate_warp<16>(p, cap, stream);
+    else if (Tmax <= 32) launch_aggregate_group<2>(p, cap, stream);   // two warps per track
+    else launch_aggregate_group<4>(p, cap, stream);                   // 33..64 frames: four warps per track
     SEAM_LAUNCHED(h, "aggregate kernel");
-  }
-
-  // K1b: out = pooled' + (r_hi + r_lo) M^T on the tensor cores
-  CUtensorMap tmRh, tmRl, tmMh, tmMl;
-  int rc;
-  if ((rc = encode_map_f32_rows(h, &tmRh, r_hi, Q, nlbtc::BM)) != SEAM_OK) return rc;
-  if ((rc = encode_map_f32_rows(h, &tmRl, r_lo, Q, nlbtc::BM)) != SEAM_OK) return rc;
-  if ((rc = encode_map_f32_rows(h, &tmMh, h->fold + Fold::M_HI, 256, nlbtc::BN)) != SEAM_OK) return rc;
-  if ((rc = encode_map_f32_rows(h, &tmMl, h->fold + Fold::M_LO, 256, nlbtc::BN)) != SEAM_OK) return rc;
-  nlbtc::Params gp;
-  gp.pooled = pooled;
-  gp.out = out;
-  gp.rows = Q;
-  {
-    ProfileScope prof(h, SEAM_KERNEL_NLB_GEMM, stream);
-    nlbtc::nlb_tc_kernel<<<(Q + nlbtc::BM - 1) / nlbtc::BM, nlbtc::THREADS, nlbtc::SMEM_BYTES, stream>>>(
-        tmRh, tmRl, tmMh, tmMl, gp);
-    SEAM_LAUNCHED(h, "nlb_tc_kernel");
   }
   return SEAM_OK;
 }
@@ -427,16 +427,11 @@ struct ScorePlan {
   size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_gmax, off_rowflag, off_rowbuf, off_cnt, off_rows, total;
 };
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-
 // The (query tile, gallery tile) grid is linearised query-major and cut into one contiguous
 // range per CTA (score_tc.cuh).  A query tile's gallery sweep is therefore shared by at most P
 // CTAs ("pieces"); each piece owns 4 candidate sub-lists per row (one per epilogue thread of
 // the row) of CAP entries, CAP >= 3 times the expected number of appends.
-static ScorePlan plan_score(int num_sms, int Q, int G, int nseed_override = -1) {
+static ScorePlan plan_score(int num_sms, int Q, int G, int nseed_override = -1, int nseed_default = 4, int cap_grid = 0) {
   ScorePlan s;
   s.num_mtiles = (Q + score::BM - 1) / score::BM;
   s.ntiles_n = (G + score::BN - 1) / score::BN;
@@ -444,12 +439,9 @@ static ScorePlan plan_score(int num_sms, int Q, int G, int nseed_override = -1) 
   if (s.ntiles_n < 1) s.ntiles_n = 1;
   s.total_tiles = (long long)s.num_mtiles * s.ntiles_n;
   s.grid = s.total_tiles < num_sms ? (int)s.total_tiles : num_sms;
-  {
-    const int cap_grid = env_int("SEAM_DEBUG_SCORE_GRID", 0);   // developer diagnostics only
-    if (cap_grid > 0 && cap_grid < s.grid) s.grid = cap_grid;
-  }
+  if (cap_grid > 0 && cap_grid < s.grid) s.grid = cap_grid;   // developer diagnostics only (seam_create reads the override)
   if (s.grid > score::MAX_GRID) s.grid = score::MAX_GRID;
-  s.nseed = nseed_override >= 0 ? nseed_override : env_int("SEAM_SCORE_NSEED", 4);
+  s.nseed = nseed_override >= 0 ? nseed_override : nseed_default;
   // Cost-balanced contiguous ranges.  A tile costs 1; a segment start costs SEG_COST (query tile load,
   // epilogue hand-over); a segment that holds its row's first gallery tile -- or is all a CTA has --
   // also sweeps min(nseed, length) threshold-only sample tiles (score_tc.cuh, segment_before).  walk()
@@ -565,12 +557,12 @@ static ScorePlan plan_score(int num_sms, int Q, int G, int nseed_override = -1) 
 size_t seam_score_workspace_bytes(const seam_handle* h, int Q, int G, int k) {
   (void)k;
   if (!h || Q <= 0 || G <= 0) return 256;
-  return plan_score(h->num_sms, Q, G).total;
+  return plan_score(h->num_sms, Q, G, -1, h->score_nseed, h->dbg_score_grid).total;
 }
 
 int seam_score_plan(const seam_handle* h, int Q, int G, int64_t* out) {
   if (!h || !out || Q <= 0 || G <= 0) return SEAM_ERR_BAD_ARG;
-  const ScorePlan s = plan_score(h->num_sms, Q, G);
+  const ScorePlan s = plan_score(h->num_sms, Q, G, -1, h->score_nseed, h->dbg_score_grid);
   const int64_t v[14] = {s.num_mtiles, s.ntiles_n, s.grid, s.P, s.CAP, (int64_t)s.off_a16,
                          (int64_t)s.off_rq, (int64_t)s.off_anorm, (int64_t)s.off_thr, (int64_t)s.off_rowcnt,
                          (int64_t)s.off_rowbuf, (int64_t)s.off_cnt, (int64_t)s.off_rows, (int64_t)s.total};
@@ -635,7 +627,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   if (!q || !g || !g16 || !cg || !gstat || !workspace) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_topk: null pointer");
   if (!aligned16(q) || !aligned16(g) || !aligned16(g16) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_topk: q/g/g16 need 16-byte, workspace 256-byte alignment");
-  const ScorePlan s = plan_score(h->num_sms, Q, G);
+  const ScorePlan s = plan_score(h->num_sms, Q, G, -1, h->score_nseed, h->dbg_score_grid);
   if (s.ntiles_n > (1 << 18))
     return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_topk: G=%d exceeds the 2^26 gallery rows one shard may hold", G);
   if (workspace_bytes < s.total)
@@ -690,7 +682,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   sp.rank_hi = nullptr;
   sp.rank_above = nullptr;
   // developer diagnostics: SEAM_DEBUG_CTA_NS=1 records per-CTA durations at the tail of the fallback-row list
-  sp.cta_ns = (env_int("SEAM_DEBUG_CTA_NS", 0) && (size_t)Q * 4 >= 8192)
+  sp.cta_ns = (h->dbg_cta_ns && (size_t)Q * 4 >= 8192)
                   ? reinterpret_cast<unsigned long long*>(ws + s.off_rows + (((size_t)Q * 4 - 4096) & ~(size_t)7))
                   : nullptr;
   {
@@ -789,7 +781,7 @@ int seam_rank_of_target(seam_handle* h, const float* q, int Q, const float* g, i
 
 size_t seam_rank_workspace_bytes(const seam_handle* h, int Q, int G) {
   if (!h || Q <= 0 || G <= 0) return 256;
-  return plan_score(h->num_sms, Q, G, 0).total;
+  return plan_score(h->num_sms, Q, G, 0, h->score_nseed, h->dbg_score_grid).total;
 }
 
 // Tensor-core path: prepare queries -> exact target margins + bands -> score_topk_kernel<VAR_RANK> (counts
@@ -811,7 +803,7 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
     return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_of_target_prepared: null pointer");
   if (!aligned16(q) || !aligned16(g) || !aligned16(g16) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_of_target_prepared: q/g/g16 need 16-byte, workspace 256-byte alignment");
-  const ScorePlan s = plan_score(h->num_sms, Q, G, 0);
+  const ScorePlan s = plan_score(h->num_sms, Q, G, 0, h->score_nseed, h->dbg_score_grid);
   if (s.ntiles_n > (1 << 18))
     return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_of_target_prepared: G=%d exceeds the 2^26 gallery rows one shard may hold", G);
   if (workspace_bytes < s.total)

@@ -64,9 +64,30 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+// Watchdog records: host-mapped memory (set by seam_create), so that what a timed-out wait wrote is still
+// readable by the host after the trap has killed the context.  Word 0 counts records; record i =
+// {tag, blockIdx.x, threadIdx.x, barrier shared address, parity, 0, 0, 0} at words 8 + 8 i.
+__device__ unsigned int* g_watchdog = nullptr;
+constexpr int WATCHDOG_RECORDS = 31;
+__device__ __noinline__ void watchdog_trap(uint32_t tag, uint32_t bar_addr, uint32_t parity) {
+  unsigned int* w = g_watchdog;
+  if (w) {
+    const unsigned int i = atomicAdd(w, 1u);
+    if (i < (unsigned)WATCHDOG_RECORDS) {
+      volatile unsigned int* r = w + 8 + 8 * i;
+      r[0] = tag;
+      r[1] = blockIdx.x;
+      r[2] = threadIdx.x;
+      r[3] = bar_addr;
+      r[4] = parity;
+    }
+    __threadfence_system();
+  }
+  __trap();
+}
 // Blocking wait with a wall-clock watchdog: a protocol bug traps (the launch fails with an
-// error the host reports) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// error the host reports, naming the wait by its tag) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   for (;;) {
@@ -77,7 +98,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       if (mbar_try_wait_hint(bar, parity, 20000u)) return;
     const uint64_t now = globaltimer_ns();
     if (t0 == 0) t0 = now;
-    else if (now - t0 > 4000000000ull) __trap();
+    else if (now - t0 > 2000000000ull) watchdog_trap(tag, smem_u32(bar), parity);
   }
 }
 
@@ -144,6 +165,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one 32-bit column = two K-adjacent fp16)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once every MMA previously issued by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -193,6 +226,51 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: this thread's lane (row), 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Register re-balancing between the warpgroups of a CTA (all four warps of a warpgroup execute it)
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// L2 eviction-priority policy for data that is read exactly once
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 // same, but ties the destination registers of an in-flight tcgen05.ld to the wait so the
 // compiler cannot read them before the data has landed
 __device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&r)[16]) {

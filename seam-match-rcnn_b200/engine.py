@@ -92,6 +92,14 @@ class SeamEngine:
             t = t.to(device=self.device, dtype=torch.float32).contiguous()
         return t
 
+    def watchdog_records(self):
+        """Records left by device-side wait watchdogs (empty in normal operation): a list of
+        ``{tag, block, thread, barrier, parity}``; readable even after a failed launch."""
+        buf = (C.c_uint32 * (8 * 31))()
+        n = int(self._lib.seam_watchdog_read(self._h, buf, 31))
+        return [dict(tag=int(buf[8 * i]), block=int(buf[8 * i + 1]), thread=int(buf[8 * i + 2]),
+                     barrier=int(buf[8 * i + 3]), parity=int(buf[8 * i + 4])) for i in range(n)]
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.seam_launch_count(self._h))
