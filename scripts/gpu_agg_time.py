@@ -6,14 +6,20 @@ from bench import random_init_weights
 dev = torch.device("cuda:0")
 e = pkg.SeamEngine(dev); e.load_weights(random_init_weights(dev))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+clean = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+CLEAN = os.environ.get("SEAM_FLUSH_CLEAN", "1") != "0"   # read 256 MiB after the write: L2 holds clean lines, no write-backs during the kernel
 HBM = 6542.1
-for Q, T in [(15000, 10), (100000, 10), (100000, 4), (10000, 4), (100000, 16), (50000, 32), (100000, 64), (64, 10)]:
+CASES = [(15000, 10), (100000, 10), (100000, 4), (10000, 4), (100000, 16), (50000, 32), (100000, 64), (64, 10)]
+if len(sys.argv) > 2:
+    CASES = [(int(sys.argv[1]), int(sys.argv[2]))]
+for Q, T in CASES:
     seq = torch.randn(1 + T, Q, 256, device=dev)
     for _ in range(3):
         e.aggregate(seq)
     e.profile(True)
     for _ in range(10):
         flush.fill_(1)
+        if CLEAN: clean.sum()
         e.aggregate(seq)
     torch.cuda.synchronize()
     pr = e.profile_read()

@@ -51,6 +51,17 @@ def is_stale() -> bool:
         return f.read().strip() != source_hash()
 
 
+def build_variant(name: str, defines) -> str:
+    """Developer A/B builds: the library compiled with extra -D flags into libseam_b200.<name>.so (selected at
+    run time with SEAM_B200_LIB=<path>).  Never used by the product path."""
+    out = os.path.join(HERE, f"libseam_b200.{name}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ -> libseam_b200.so (only when sources are newer). Returns the path."""
     if not force and not is_stale():

@@ -55,6 +55,7 @@ struct Meta {
   uint64_t tile_full[2];     // producers -> MMA      (NB x ARRIVALS arrivals)
   uint64_t buf_free[2];      // helpers  -> producers (HELPER_WARPS arrivals)
   uint64_t acc_full;         // MMA      -> helpers   (tcgen05.commit)
+  uint64_t m_ready;          // all warps -> MMA      (their share of M sits in tensor memory)
   unsigned int next_slot;
   uint32_t tmem_base;
 };
@@ -77,6 +78,24 @@ struct Params {
 };
 
 using ptx::treduce;
+
+// developer diagnostic (SEAM_AGG_TIMELINE builds only; the attention output is sacrificed): per-CTA
+// globaltimer stamps at slots 0..7 of an 8 x u64 record in the att buffer
+#ifdef SEAM_AGG_TIMELINE
+#define SEAM_TL(p, slot) do { if ((p).att && lane == 0) reinterpret_cast<unsigned long long*>((p).att)[blockIdx.x * 8 + (slot)] = ptx::globaltimer_ns(); } while (0)
+#else
+#define SEAM_TL(p, slot) do { } while (0)
+#endif
+#ifdef SEAM_AGG_TIMELINE3
+#define SEAM_TL3(p, slot) do { if ((p).att && lane == 0) reinterpret_cast<unsigned long long*>((p).att)[blockIdx.x * 8 + (slot)] = ptx::globaltimer_ns(); } while (0)
+#else
+#define SEAM_TL3(p, slot) do { } while (0)
+#endif
+#ifdef SEAM_AGG_TIMELINE2
+#define SEAM_TL2(p, slot) do { if ((p).att && lane == 0) reinterpret_cast<unsigned long long*>((p).att)[blockIdx.x * 8 + (slot)] = ptx::globaltimer_ns(); } while (0)
+#else
+#define SEAM_TL2(p, slot) do { } while (0)
+#endif
 
 // ---- packed fp32 pairs (FFMA2 / FMUL2): the streaming pass is bound by instruction issue
 typedef unsigned long long u64;
@@ -185,6 +204,55 @@ __device__ __forceinline__ void store_r2(uint8_t* rt, int pos, int c, float r0, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// M -> tensor memory, by ALL warps of the CTA (a warp can only write the 32 lanes of its own quarter,
+// warp % 4): the 30 chunks of 16 columns (M1: 2 halves x 8, M2: 2 halves x 7) of a quarter are dealt out
+// to the NWARPS / 4 warps that share it, two chunks (32 coalesced loads per thread) in flight at a time.
+// A serial load by the four helper warps alone took 22 dependent round trips (~17 us, the floor of the
+// kernel at small Q); producers do their share while their first frames are in flight.
+#ifdef SEAM_AGG_HELPER_INIT      // developer A/B: the helper warps alone load M
+#define SEAM_AGG_INIT_WARPS(all) HELPER_WARPS
+#else
+#define SEAM_AGG_INIT_WARPS(all) (all)
+#endif
+template <int NWARPS, int INFLIGHT>
+__device__ __forceinline__ void load_m_tmem(const Params& p, Meta* meta, int warp, int lane) {
+  constexpr int NPART = NWARPS / 4, NCHUNK = 16 + 2 * (KT / 32);
+  const int part = warp >> 2, quarter = warp & 3;
+  const uint32_t lane_base = meta->tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t* f32 = reinterpret_cast<const uint32_t*>(p.fold) + quarter * 32 + lane;
+  auto locate = [&](int c, const uint32_t*& src, uint32_t& col) {
+    if (c < 16) {
+      const int h = c >> 3, c0 = (c & 7) * 16;
+      src = f32 + Fold::M1_IMG + (h * 128 + c0) * 128;
+      col = COL_M1 + h * 128 + c0;
+    } else {
+      const int cc = c - 16, h = cc / (KT / 32), c0 = (cc % (KT / 32)) * 16;
+      src = f32 + Fold::M2_IMG + (h * (KT / 2) + c0) * 128;
+      col = COL_M2 + h * (KT / 2) + c0;
+    }
+  };
+#pragma unroll 1
+  for (int c = part; c < NCHUNK; c += INFLIGHT * NPART) {
+    uint32_t v[INFLIGHT][16], col[INFLIGHT];
+#pragma unroll
+    for (int u = 0; u < INFLIGHT; ++u) {
+      const uint32_t* src;
+      const int cu = c + u * NPART;
+      locate(cu < NCHUNK ? cu : c, src, col[u]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[u][j] = __ldg(src + j * 128);
+    }
+#pragma unroll
+    for (int u = 0; u < INFLIGHT; ++u)
+      if (c + u * NPART < NCHUNK) ptx::tmem_st_x16(lane_base + col[u], v[u]);
+  }
+  ptx::tmem_st_wait();
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(&meta->m_ready);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Helper warps: tensor-memory set-up, one MMA batch per NB published tracks, read-back + store.
 //   units        producer units (warps or warp groups) of this CTA, unit u handles tracks
 //                first0 + u, first0 + u + stride, ...
@@ -196,35 +264,14 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
   const uint32_t tmem = meta->tmem_base;
   const uint32_t lane_base = tmem + ((uint32_t)(hw * 32) << 16);
   const uint32_t* f32 = reinterpret_cast<const uint32_t*>(p.fold);
-  const int row = hw * 32 + lane;                        // row of a 128-row half this thread owns in tensor memory
 
-  // ---- M1, M2 -> tensor memory (coalesced reads of the pre-arranged images), M2's last k's -> shared memory
+  // ---- M2's last k's -> shared memory (the tensor-memory part of M is loaded by all warps, load_m_tmem)
   {
-    uint32_t v[32];
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = __ldg(f32 + Fold::M1_IMG + (h * 128 + c0 + c) * 128 + row);
-        ptx::tmem_st_x32(lane_base + COL_M1 + h * 128 + c0, v);
-      }
-#pragma unroll 1
-      for (int c0 = 0; c0 < KT / 2; c0 += 16) {
-        uint32_t w[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) w[c] = __ldg(f32 + Fold::M2_IMG + (h * (KT / 2) + c0 + c) * 128 + row);
-        ptx::tmem_st_x16(lane_base + COL_M2 + h * (KT / 2) + c0, w);
-      }
-    }
     const uint4* tsrc = reinterpret_cast<const uint4*>(f32 + Fold::M2_TAIL);
     uint4* tdst = reinterpret_cast<uint4*>(fz + OFF_TAIL);
     for (int i = hw * 32 + lane; i < (int)(TAIL_BYTES / 16); i += HELPER_WARPS * 32) tdst[i] = __ldg(tsrc + i);
     ptx::fence_proxy_async_smem();
-    ptx::tmem_st_wait();
-    ptx::tc_fence_before();
     ptx::named_bar_sync(1, HELPER_WARPS * 32);
-    ptx::tc_fence_after();
   }
 
   // tracks this CTA handles (static strided assignment of the producers)
@@ -233,7 +280,11 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
     const long long f = first0 + u;
     if (f < p.Q) n_cta += (p.Q - f + stride - 1) / stride;
   }
+#ifdef SEAM_AGG_DIAG_NO_PUBLISH     // developer diagnostic (wrong results): streaming pass alone
+  const int nbatch = 0;
+#else
   const int nbatch = (int)((n_cta + NB - 1) / NB);
+#endif
   const float ms_inv = p.fold[Fold::CONSTS + 9];        // 1 / S
   const uint32_t rt_addr = ptx::smem_u32(fz + OFF_RT), tail_addr = ptx::smem_u32(fz + OFF_TAIL);
   constexpr uint32_t idesc = ptx::umma_idesc(0 /*fp16*/, 128, NB);
@@ -243,17 +294,26 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
     const int buf = b & 1;
     const int cnt = (b == nbatch - 1) ? (int)(n_cta - (long long)b * NB) : NB;
     if (hw == 0) {
-      // ------------------------------------------------ MMA issue (one lane)
-      if (lane == 0) {
+      // ------------------------------------------------ MMA issue (one elected lane of the converged warp)
+      if (lane == 0)
         for (int i = 0; i < (NB - cnt) * ARRIVALS; ++i) ptx::mbar_arrive(&meta->tile_full[buf]);   // slots nobody fills
-        ptx::mbar_wait(&meta->tile_full[buf], (uint32_t)(b >> 1) & 1u, 102);
-        ptx::tc_fence_after();
+      ptx::mbar_wait(&meta->tile_full[buf], (uint32_t)(b >> 1) & 1u, 102);
+      if (b == 0) ptx::mbar_wait(&meta->m_ready, 0u, 108);
+      if (b == 0) SEAM_TL(p, 3);
+      if (b == 3) SEAM_TL3(p, 0);
+      if (b == 4) SEAM_TL3(p, 5);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
         const uint32_t r1 = rt_addr + buf * RT_BYTES, r2 = r1 + RT_TERM_BYTES;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           const uint32_t d = tmem + COL_D + h * NB;
 #pragma unroll
+#ifdef SEAM_AGG_DIAG_NO_MMA      // developer diagnostic (wrong results): one MMA per half instead of 48
+          for (int ks = 0; ks < 1; ++ks) {
+#else
           for (int ks = 0; ks < 16; ++ks) {               // k-steps of 16
+#endif
             const uint32_t boff = (uint32_t)(ks >> 2) * (NB * 128) + (uint32_t)(ks & 3) * 32;
             const uint64_t b1 = ptx::umma_desc_k_sw128(r1 + boff), b2 = ptx::umma_desc_k_sw128(r2 + boff);
             const uint32_t a1 = tmem + COL_M1 + h * 128 + ks * 8;
@@ -268,11 +328,15 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
           }
         }
         ptx::umma_commit(&meta->acc_full);
+        if (b == 0) SEAM_TL(p, 4);
+        if (b == nbatch - 1) SEAM_TL(p, 5);
       }
+      if (b == 3) SEAM_TL3(p, 1);
       __syncwarp();
     }
     // ---------------------------------------------------- read-back: thread = channel, register = track
     ptx::mbar_wait(&meta->acc_full, (uint32_t)b & 1u, 103);
+    if (hw == 0 && b == 3) SEAM_TL3(p, 2);
     ptx::mbar_wait(&meta->tile_full[buf], (uint32_t)(b >> 1) & 1u, 104);   // acquire what the producers published (already complete)
     ptx::tc_fence_after();
     uint32_t d0[16], d1[16];
@@ -282,6 +346,7 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
     ptx::tmem_ld_wait_x16(d1);
     ptx::tc_fence_before();
     ptx::named_bar_sync(1, HELPER_WARPS * 32);           // the accumulator may be overwritten by the next batch
+    if (hw == 0 && b == 3) SEAM_TL3(p, 3);
     const int ch = hw * 32 + lane;
     const float* pool = reinterpret_cast<const float*>(fz + OFF_POOL + buf * POOL_BYTES);
 #pragma unroll
@@ -304,6 +369,8 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
     }
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&meta->buf_free[buf]);
+    if (hw == 0 && b == nbatch - 1) SEAM_TL(p, 6);
+    if (hw == 0 && b == 3) SEAM_TL3(p, 4);
   }
 }
 
@@ -317,6 +384,7 @@ __device__ __forceinline__ void fused_setup(uint8_t* fz, int warp, int helper0) 
       ptx::mbar_init(&meta->buf_free[i], HELPER_WARPS);
     }
     ptx::mbar_init(&meta->acc_full, 1);
+    ptx::mbar_init(&meta->m_ready, SEAM_AGG_INIT_WARPS(blockDim.x >> 5));
     meta->next_slot = 0u;
     ptx::fence_mbar_init();
   }
@@ -380,56 +448,77 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
     for (int i = 0; i < SLOTS; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
   }
+  if (warp == 0) SEAM_TL(p, 0);
+  if (warp == 0) SEAM_TL2(p, 0);
+  __syncwarp();
+  const int Tmax = p.Tmax;
+  const long long first = first0 + warp;
+  const uint64_t pol = ptx::policy_evict_first();       // frames are read exactly once
+
+  // A track's length comes from lens[] or from its mask row.  peek() only issues that (dependent) load --
+  // one track ahead of its use -- and issue() turns the loaded word into the length and starts the copies.
+  auto peek = [&](long long track) -> int {
+    if (track >= p.Q) return 0;
+    if (p.lens) return p.lens[track];
+    if (p.mask) return lane <= Tmax ? (int)p.mask[(size_t)track * (1 + Tmax) + lane] : 0;
+    return 0;
+  };
+  auto issue = [&](long long track, int slot, int raw) {
+    int len = 0;
+    if (track < p.Q) {
+      if (p.lens) {
+        len = raw;
+      } else if (p.mask) {
+        // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
+        const uint32_t b = __ballot_sync(ptx::FULL_MASK, raw != 0);
+        const int end = b ? __ffs(b) - 1 : 1 + Tmax;
+        len = end - 1;
+      } else {
+        len = Tmax;
+      }
+      len = max(0, min(len, Tmax));
+    }
+    if (lane == 0) {
+      slot_len[slot] = len;
+      if (len > 0) ptx::mbar_arrive_expect_tx(&bars[slot], (uint32_t)len * (D * 4));
+      else ptx::mbar_arrive(&bars[slot]);
+    }
+    __syncwarp();
+    if (lane < len) {
+      const float* src = p.seq + (long long)(lane + 1) * p.frame_stride + track * p.track_stride;
+#ifdef SEAM_AGG_NO_HINT
+      ptx::bulk_load_1d(xbuf + ((size_t)slot * TR + lane) * D, src, D * 4, &bars[slot]);
+#else
+      ptx::bulk_load_1d_hint(xbuf + ((size_t)slot * TR + lane) * D, src, D * 4, &bars[slot], pol);
+#endif
+    }
+  };
+
+  // the first tracks are requested before anything else happens in this CTA (barrier set-up, tensor-memory
+  // allocation, register re-balancing and a cold instruction cache cost ~3 us)
+  constexpr int AHEAD = SLOTS == 1 ? 1 : SLOTS - 1;     // tracks in flight ahead of the one being processed
+  int raw_next = 0;
+  if (warp < NW) {
+#pragma unroll 1
+    for (int i = 0; i < AHEAD; ++i) issue(first + i * stride, i, peek(first + i * stride));
+    raw_next = peek(first + (long long)AHEAD * stride);
+  }
   fused_setup<1>(fz, warp, NW);
+  if (warp == 0) SEAM_TL2(p, 1);
 
   if (warp >= NW) {
     ptx::reg_dec<Cfg<TR>::REGS_H>();
+    load_m_tmem<SEAM_AGG_INIT_WARPS(NW + HELPER_WARPS), 2>(p, meta, SEAM_AGG_INIT_WARPS(NW + HELPER_WARPS) == HELPER_WARPS ? warp - NW : warp, lane);
     helper_role<1, true>(p, fz, warp - NW, lane, NW, first0, stride);
   } else {
     ptx::reg_inc<Cfg<TR>::REGS_P>();
-    const int Tmax = p.Tmax;
-    const long long first = first0 + warp;
-    const uint64_t pol = ptx::policy_evict_first();       // frames are read exactly once
-
-    // A track's length comes from lens[] or from its mask row.  peek() only issues that (dependent) load --
-    // one track ahead of its use -- and issue() turns the loaded word into the length and starts the copies.
-    auto peek = [&](long long track) -> int {
-      if (track >= p.Q) return 0;
-      if (p.lens) return p.lens[track];
-      if (p.mask) return lane <= Tmax ? (int)p.mask[(size_t)track * (1 + Tmax) + lane] : 0;
-      return 0;
-    };
-    auto issue = [&](long long track, int slot, int raw) {
-      int len = 0;
-      if (track < p.Q) {
-        if (p.lens) {
-          len = raw;
-        } else if (p.mask) {
-          // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
-          const uint32_t b = __ballot_sync(ptx::FULL_MASK, raw != 0);
-          const int end = b ? __ffs(b) - 1 : 1 + Tmax;
-          len = end - 1;
-        } else {
-          len = Tmax;
-        }
-        len = max(0, min(len, Tmax));
-      }
-      if (lane == 0) {
-        slot_len[slot] = len;
-        if (len > 0) ptx::mbar_arrive_expect_tx(&bars[slot], (uint32_t)len * (D * 4));
-        else ptx::mbar_arrive(&bars[slot]);
-      }
-      __syncwarp();
-      if (lane < len) {
-        const float* src = p.seq + (long long)(lane + 1) * p.frame_stride + track * p.track_stride;
-        ptx::bulk_load_1d_hint(xbuf + ((size_t)slot * TR + lane) * D, src, D * 4, &bars[slot], pol);
-      }
-    };
-
-    constexpr int AHEAD = SLOTS == 1 ? 1 : SLOTS - 1;     // tracks in flight ahead of the one being processed
-#pragma unroll 1
-    for (int i = 0; i < AHEAD; ++i) issue(first + i * stride, i, peek(first + i * stride));
-    int raw_next = peek(first + (long long)AHEAD * stride);
+    if (warp == 0) SEAM_TL2(p, 2);
+    if (warp == 0) SEAM_TL2(p, 3);
+#ifndef SEAM_AGG_HELPER_INIT
+    load_m_tmem<NW + HELPER_WARPS, (TR >= 10 ? 4 : 2)>(p, meta, warp, lane);   // while the first frames are in flight
+    if (warp == 0) SEAM_TL(p, 1);
+    if (warp == 0) SEAM_TL2(p, 4);
+#endif
 
     const float* fold = p.fold;
     const Vec8 ut = load_vec8(fold + Fold::U_THETA, lane);
@@ -453,6 +542,10 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
         raw_next = peek(track + (long long)SLOTS * stride);
       }
       ptx::mbar_wait(&bars[slot], phase, 105);
+      if (warp == 0 && it == 0) SEAM_TL(p, 2);
+      if (warp == 0 && it == 0) SEAM_TL2(p, 5);
+      if (warp == 0 && it == 1) SEAM_TL2(p, 6);
+      if (warp == 0 && it == 2) SEAM_TL2(p, 7);
       const int len = slot_len[slot];
       const float* xs = xbuf + (size_t)slot * TR * D;
 
@@ -535,7 +628,9 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
         const float qsum = ptx::warp_sum(q_j);
         __syncwarp();                                    // all lanes have read the a_t
         if (lane < TR) *reinterpret_cast<float4*>(scal + 4 * lane) = make_float4(p_t, p_t, q_j, q_j);
+#if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3)
         if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
+#endif
         __syncwarp();
 
         // ---- weighted sums over frames, 8 channels per lane
@@ -571,7 +666,13 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
         mx = ptx::warp_max(mx);
         float inv;
         const float s = track_scale(mx, &inv);
+#ifdef SEAM_AGG_DIAG_NO_PUBLISH
+        if (mx == 123.456f) p.out[track] = s + po0.x + po1.y + r0.x + r1.w;
+        return;
+#endif
+        if (warp == 0 && it == 5) SEAM_TL3(p, 6);
         const Slot sl = claim_slot(meta, lane);
+        if (warp == 0 && it == 5) SEAM_TL3(p, 7);
         uint8_t* rt = fz + OFF_RT + sl.buf * RT_BYTES;
         store_r4(rt, sl.pos, 4 * lane, r0, s);
         store_r4(rt, sl.pos, 128 + 4 * lane, r1, s);
@@ -591,6 +692,7 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
     }
   }
   fused_teardown(fz, warp, NW);
+  if (warp == 0) SEAM_TL(p, 7);
 }
 
 
@@ -643,55 +745,67 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
     ptx::mbar_init(&s.bar[warp], 1);
     ptx::fence_mbar_init();
   }
+  __syncwarp();
+  const int pw = warp < GWARPS ? warp : 0;            // helper warps never use what follows
+  const int grp = pw / GW, wg = pw % GW;
+  GroupSmem<GW>& gs = s.g[grp];
+  float* xs = &s.x[pw][0][0];
+  uint64_t* bar = &s.bar[pw];
+  const int Tmax = p.Tmax;
+  const uint32_t bar_id = 2 + grp;                     // named barrier 1 belongs to the helpers
+  const long long first = first0 + grp;
+  const uint64_t pol = ptx::policy_evict_first();
+
+  // length of a track (every warp of the group derives it on its own)
+  auto track_len = [&](long long track) -> int {
+    if (track >= p.Q) return 0;
+    int len;
+    if (p.lens) {
+      len = p.lens[track];
+    } else if (p.mask) {
+      // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
+      const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
+      const uint32_t b0 = __ballot_sync(ptx::FULL_MASK, lane <= Tmax && m[lane] != 0);
+      const uint32_t b1 = __ballot_sync(ptx::FULL_MASK, 32 + lane <= Tmax && m[min(32 + lane, Tmax)] != 0);
+      const uint32_t b2 = __ballot_sync(ptx::FULL_MASK, lane == 0 && Tmax >= 64 && m[min(64, Tmax)] != 0);
+      const int end = b0 ? __ffs(b0) - 1 : b1 ? 32 + __ffs(b1) - 1 : b2 ? 64 : 1 + Tmax;
+      len = end - 1;
+    } else {
+      len = Tmax;
+    }
+    return max(0, min(len, Tmax));
+  };
+  // start the copies of this warp's frame block of one track
+  auto issue = [&](long long track, int len) {
+    const int nw = max(0, min(len - FB * wg, FB));
+    if (lane == 0) {
+      if (nw > 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nw * (D * 4));
+      else ptx::mbar_arrive(bar);
+    }
+    __syncwarp();
+    if (lane < nw) {
+      const float* src = p.seq + (long long)(FB * wg + lane + 1) * p.frame_stride + track * p.track_stride;
+#ifdef SEAM_AGG_NO_HINT
+      ptx::bulk_load_1d(xs + (size_t)lane * D, src, D * 4, bar);
+#else
+      ptx::bulk_load_1d_hint(xs + (size_t)lane * D, src, D * 4, bar, pol);
+#endif
+    }
+  };
+  // the first track is requested before the CTA-wide set-up
+  int len = 0;
+  if (warp < GWARPS) {
+    len = track_len(first);
+    issue(first, len);
+  }
   fused_setup<GW>(fz, warp, GWARPS);
 
   if (warp >= GWARPS) {
     ptx::reg_dec<GREGS_H>();
+    load_m_tmem<SEAM_AGG_INIT_WARPS(GWARPS + HELPER_WARPS), 2>(p, meta, SEAM_AGG_INIT_WARPS(GWARPS + HELPER_WARPS) == HELPER_WARPS ? warp - GWARPS : warp, lane);
     helper_role<GW, false>(p, fz, warp - GWARPS, lane, GROUPS_PER_CTA, first0, stride);
   } else {
     ptx::reg_inc<GREGS_P>();
-    const int grp = warp / GW, wg = warp % GW;
-    GroupSmem<GW>& gs = s.g[grp];
-    float* xs = &s.x[warp][0][0];
-    uint64_t* bar = &s.bar[warp];
-    const int Tmax = p.Tmax;
-    const uint32_t bar_id = 2 + grp;                     // named barrier 1 belongs to the helpers
-    const long long first = first0 + grp;
-    const uint64_t pol = ptx::policy_evict_first();
-
-    // length of a track (every warp of the group derives it on its own)
-    auto track_len = [&](long long track) -> int {
-      if (track >= p.Q) return 0;
-      int len;
-      if (p.lens) {
-        len = p.lens[track];
-      } else if (p.mask) {
-        // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
-        const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
-        const uint32_t b0 = __ballot_sync(ptx::FULL_MASK, lane <= Tmax && m[lane] != 0);
-        const uint32_t b1 = __ballot_sync(ptx::FULL_MASK, 32 + lane <= Tmax && m[min(32 + lane, Tmax)] != 0);
-        const uint32_t b2 = __ballot_sync(ptx::FULL_MASK, lane == 0 && Tmax >= 64 && m[min(64, Tmax)] != 0);
-        const int end = b0 ? __ffs(b0) - 1 : b1 ? 32 + __ffs(b1) - 1 : b2 ? 64 : 1 + Tmax;
-        len = end - 1;
-      } else {
-        len = Tmax;
-      }
-      return max(0, min(len, Tmax));
-    };
-    // start the copies of this warp's frame block of one track
-    auto issue = [&](long long track, int len) {
-      const int nw = max(0, min(len - FB * wg, FB));
-      if (lane == 0) {
-        if (nw > 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nw * (D * 4));
-        else ptx::mbar_arrive(bar);
-      }
-      __syncwarp();
-      if (lane < nw) {
-        const float* src = p.seq + (long long)(FB * wg + lane + 1) * p.frame_stride + track * p.track_stride;
-        ptx::bulk_load_1d_hint(xs + (size_t)lane * D, src, D * 4, bar, pol);
-      }
-    };
-
     const float* fold = p.fold;
     const Vec8 ut = load_vec8(fold + Fold::U_THETA, lane);
     const Vec8 up = load_vec8(fold + Fold::U_PHI, lane);
@@ -702,8 +816,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
     const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
                          : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
 
-    int len = track_len(first);
-    issue(first, len);
+#ifndef SEAM_AGG_HELPER_INIT
+    load_m_tmem<GWARPS + HELPER_WARPS, 2>(p, meta, warp, lane);   // while the first frames are in flight
+#endif
     int it = 0;
 #pragma unroll 1
     for (long long track = first; track < p.Q; track += stride, ++it) {
@@ -765,7 +880,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
       for (int w = 1; w < GW; ++w) z += gs.red_sum[w];
       const float p_t = valid ? e_t / z : 0.f;
       if (half == 0) gs.scal[F][1] = p_t;
+#if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3)
       if (p.att && half == 0 && F < Tmax) p.att[(size_t)track * Tmax + F] = p_t;
+#endif
       ptx::named_bar_sync(bar_id, GW * 32);                       // #4 all p_t are visible
       float q_j = 0.f;
       if (len > 1 && valid) {
@@ -804,10 +921,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
         if (lane == 0) {
           gs.red_q[wg] = qsum_w;
           gs.red_rmax[wg] = pm;
+#ifndef SEAM_AGG_DIAG_NO_PUBLISH
           if (wg == 0) gs.slot = atomicAdd(&meta->next_slot, 1u);
+#endif
         }
       }
       ptx::named_bar_sync(bar_id, GW * 32);                       // #5 partial sums, maxima and the slot are visible
+#ifdef SEAM_AGG_DIAG_NO_PUBLISH
+      if (gs.red_rmax[0] == 123.456f) p.out[track] = gs.part[0][lane];
+      len = len_next;
+      continue;
+#endif
 
       // ---- warp w finishes channels [CW w, CW (w+1)), CW = 256 / GW, and publishes them
       {
@@ -819,7 +943,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
         for (int w = 1; w < GW; ++w) rb += gs.red_rmax[w];
         float inv;
         const float scale = track_scale(rb, &inv);
+        if (warp == 0 && it == 40) SEAM_TL3(p, 6);
         ptx::mbar_wait(&meta->buf_free[buf], ((batch >> 1) & 1u) ^ 1u, 107);
+        if (warp == 0 && it == 40) SEAM_TL3(p, 7);
         uint8_t* rt = fz + OFF_RT + buf * RT_BYTES;
         constexpr int CW = D / GW;
 #pragma unroll
