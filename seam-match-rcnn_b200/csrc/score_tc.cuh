@@ -392,21 +392,30 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop (converged), one elected lane issues: uniform-datapath instructions
+    // (UTMALDG, UTCHMMA, SYNCS) inside a divergent `lane == 0` region are expanded by the compiler into
+    // a per-active-lane loop of ~14 instructions each.
+    {
       uint32_t stage = 0, sphase = 0, iphase = 0;
       long long t = t_end, next;
       while (t > t_begin) {
         const Segment sg = segment_before(p, t_begin, t, t_end, next);
         ptx::mbar_wait(a_empty, iphase ^ 1);
-        ptx::mbar_arrive_expect_tx(a_full, NKB * A_KB_BYTES);
-        for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, sg.m * BM);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(a_full, NKB * A_KB_BYTES);
+          for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, sg.m * BM);
+        }
+        __syncwarp();
         const int n = sg.count();
         for (int i = 0; i < n; ++i) {
           const int nt = sg.tile(i);
           for (int kb = 0; kb < NKB; ++kb) {
             ptx::mbar_wait(&empty[stage], sphase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full[stage], B_ST_BYTES);
-            ptx::tma_load_2d(sB + stage * B_ST_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&full[stage], B_ST_BYTES);
+              ptx::tma_load_2d(sB + stage * B_ST_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
+            }
+            __syncwarp();
             if (++stage == NSTAGE) {
               stage = 0;
               sphase ^= 1;
@@ -418,8 +427,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
+    // ================================================================= MMA issuer (converged warp, one elected lane)
+    {
       constexpr uint32_t idesc = ptx::umma_idesc(0 /*fp16*/, BM, BN);
       const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
       uint32_t stage = 0, sphase = 0, iphase = 0, acc = 0, aphase = 0;
@@ -435,25 +444,29 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int kb = 0; kb < NKB; ++kb) {
             ptx::mbar_wait(&full[stage], sphase);
             ptx::tc_fence_after();
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t ad = ptx::umma_desc_k_sw128(a_addr + kb * A_KB_BYTES + k * 32);
-              const uint64_t bd = ptx::umma_desc_k_sw128(b_addr + stage * B_ST_BYTES + k * 32);
-              ptx::umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t ad = ptx::umma_desc_k_sw128(a_addr + kb * A_KB_BYTES + k * 32);
+                const uint64_t bd = ptx::umma_desc_k_sw128(b_addr + stage * B_ST_BYTES + k * 32);
+                ptx::umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              ptx::umma_commit(&empty[stage]);
+              if (kb == NKB - 1) ptx::umma_commit(&t_full[acc]);
             }
-            ptx::umma_commit(&empty[stage]);
+            __syncwarp();
             if (++stage == NSTAGE) {
               stage = 0;
               sphase ^= 1;
             }
           }
-          ptx::umma_commit(&t_full[acc]);
           if (++acc == 2) {
             acc = 0;
             aphase ^= 1;
           }
         }
-        ptx::umma_commit(a_empty);
+        if (ptx::elect_one()) ptx::umma_commit(a_empty);
+        __syncwarp();
         iphase ^= 1;
         t = next;
       }
