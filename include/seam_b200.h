@@ -36,7 +36,7 @@ enum seam_status {
   SEAM_ERR_STATE = 4,        /* weights not loaded, workspace too small */
 };
 
-enum { SEAM_D = 256, SEAM_DI = 128, SEAM_MAX_T = 64, SEAM_MAX_K = 32 };
+enum { SEAM_D = 256, SEAM_DI = 128, SEAM_MAX_T = 64, SEAM_MAX_K = 32, SEAM_MAX_WORLD = 8 };
 
 /* ABI version of this header (bumped on any signature change). */
 int seam_abi_version(void);
@@ -189,6 +189,54 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
  * softmax(0, margin)[1], recomputed bit-identically, so shards need only exchange margins and indices. */
 int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, const int32_t* idx, int N, int Q,
                     int k, float* out_score, float* out_margin, int32_t* out_idx, void* stream);
+
+/* ---- gallery-sharded search over the GPUs of one box --------------------------
+ * One process per GPU; rank r holds gallery rows [r G/N, (r+1) G/N) and OWNS queries [q_lo[r], q_lo[r+1]): it
+ * aggregates their tracks and merges their per-shard top-k lists.  The kernels exchange data themselves: the
+ * aggregation kernel stores every descriptor into the q_all buffer of every rank, the re-score kernels store a
+ * query's list into the list buffer of its owner, the merge stores the merged rows into every rank's final
+ * buffers -- plain stores into peer-mapped memory (NVLink / NVSwitch), ordered by flag words (release / acquire
+ * at system scope), no collective call, no barrier kernel, no copy (csrc/exchange.cuh).  The reference has no
+ * multi-GPU retrieval path; its torch.distributed use (stuffs/utils.py:340) is training-only.
+ *
+ * All pointers are DEVICE pointers valid on the calling rank; entry [r] of a table addresses rank r's buffer
+ * (entry [rank] the local one).  The caller allocates them in peer-mapped memory (torch symmetric memory in the
+ * Python host), zero-fills flags / done and sets *step = 1 once; the library advances *step.
+ *   q_all        (2, Q, 256) fp32 per rank      descriptors, double-buffered by step parity
+ *   list_margin  (2, world, own_max, k) fp32    lists for the queries the rank owns (own_max = largest ownership)
+ *   list_idx     (2, world, own_max, k) int32
+ *   final_*      (Q, k) per rank, or all NULL: then seam_sharded_merge writes the owner's rows to its out_* only
+ *   flags        (3, SEAM_MAX_WORLD) uint32 per rank;  step (1), done (3) uint32, local to the rank            */
+typedef struct seam_exchange {
+  int32_t world, rank, Q, k, own_max;
+  int32_t q_lo[SEAM_MAX_WORLD + 1];
+  float* q_all[SEAM_MAX_WORLD];
+  float* list_margin[SEAM_MAX_WORLD];
+  int32_t* list_idx[SEAM_MAX_WORLD];
+  float* final_score[SEAM_MAX_WORLD];
+  float* final_margin[SEAM_MAX_WORLD];
+  int32_t* final_idx[SEAM_MAX_WORLD];
+  uint32_t* flags[SEAM_MAX_WORLD];
+  uint32_t* step;
+  uint32_t* done;
+} seam_exchange;
+
+/* seam_aggregate for tracks [row0, row0 + Qlocal) of the step's Q queries (a rank may pass its tracks in several
+ * calls, e.g. as they arrive from the host): descriptors go to rows row0.. of every rank's q_all; the call with
+ * last != 0 tells the other ranks that this rank's descriptors are complete. */
+int seam_sharded_aggregate(seam_handle* h, const seam_exchange* x, const float* seq, const uint8_t* mask,
+                           const int32_t* lens, int Tmax, int Qlocal, int64_t frame_stride, int64_t track_stride,
+                           int row0, int last, float* att, void* stream);
+/* seam_score_topk of all Q queries (this rank's q_all, once every rank's descriptors have landed) against the
+ * rank's prepared gallery shard; the top-k rows go to the queries' owners.  Workspace as seam_score_topk. */
+int seam_sharded_score_topk(seam_handle* h, const seam_exchange* x, const float* g, const void* g16, const float* cg,
+                            const float* gstat, int G, int index_offset, int32_t* stats, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Merges the world lists of the queries this rank owns and ends the step.  With final buffers in the exchange every
+ * rank holds the complete (Q,k) result when its stream reaches the end of this call; without, out_* (own,k) receive
+ * the owner's rows. */
+int seam_sharded_merge(seam_handle* h, const seam_exchange* x, float* out_score, float* out_margin, int32_t* out_idx,
+                       void* stream);
 
 /* Host -> device upload of a slice of tracks, tracks [lo, hi) of a HOST x3_1_seq (1+Tmax, Q, 256) fp32
  * (the reference keeps every feature in host memory between the detector and the scorer,

@@ -20,6 +20,7 @@ KERNELS = {"aggregate": 0, "nlb_gemm": 1, "prep_queries": 2, "score": 3, "rescor
            "prep_gallery": 6}
 SEAM_MAX_T = 64
 SEAM_MAX_K = 32
+SEAM_MAX_WORLD = 8
 
 
 class SeamError(RuntimeError):
@@ -35,6 +36,18 @@ class SeamWeights(C.Structure):
     FIELDS = ("theta_w", "theta_b", "phi_w", "phi_b", "g_w", "g_b", "W_w", "W_b", "concat_w",
               "att_w", "att_b", "last_w", "last_b")
     _fields_ = [(n, C.c_void_p) for n in FIELDS]
+
+
+class SeamExchange(C.Structure):
+    """struct seam_exchange (include/seam_b200.h): the peer-mapped buffers of the gallery-sharded search."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("Q", C.c_int32), ("k", C.c_int32), ("own_max", C.c_int32),
+                ("q_lo", C.c_int32 * (SEAM_MAX_WORLD + 1)),
+                ("q_all", C.c_void_p * SEAM_MAX_WORLD),
+                ("list_margin", C.c_void_p * SEAM_MAX_WORLD), ("list_idx", C.c_void_p * SEAM_MAX_WORLD),
+                ("final_score", C.c_void_p * SEAM_MAX_WORLD), ("final_margin", C.c_void_p * SEAM_MAX_WORLD),
+                ("final_idx", C.c_void_p * SEAM_MAX_WORLD),
+                ("flags", C.c_void_p * SEAM_MAX_WORLD),
+                ("step", C.c_void_p), ("done", C.c_void_p)]
 
 
 # field of seam_weights -> key in TemporalAggregationNLB.state_dict()
@@ -107,6 +120,13 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_rank_workspace_bytes.argtypes = [vp, i32, i32]
     lib.seam_rank_of_target_prepared.restype = i32
     lib.seam_rank_of_target_prepared.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]
+    xp = C.POINTER(SeamExchange)
+    lib.seam_sharded_aggregate.restype = i32
+    lib.seam_sharded_aggregate.argtypes = [vp, xp, vp, vp, vp, i32, i32, i64, i64, i32, i32, vp, vp]
+    lib.seam_sharded_score_topk.restype = i32
+    lib.seam_sharded_score_topk.argtypes = [vp, xp, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]
+    lib.seam_sharded_merge.restype = i32
+    lib.seam_sharded_merge.argtypes = [vp, xp, vp, vp, vp, vp]
     lib.seam_upload_tracks.restype = i32
     lib.seam_upload_tracks.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.seam_merge_topk.restype = i32

@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <type_traits>
 #include <cuda_fp16.h>
+#include "exchange.cuh"
 #include "fold.cuh"
 #include "sm100_ptx.cuh"
 
@@ -75,7 +76,15 @@ struct Params {
   const float* fold;
   float* out;      // (Q,256)
   float* att;      // (Q,Tmax) or null
+  // gallery-sharded search (exchange.cuh): the descriptors of this rank's tracks go to row x_row0 + track of the
+  // current-parity q_all buffer of EVERY rank; the launch that holds the rank's last tracks (x_last) signals
+  int x_on, x_last, x_row0;
+  xchg::Exchange x;
 };
+// where this rank's own copy of the descriptors lives
+__device__ __forceinline__ float* local_out(const Params& p, uint32_t xstep) {
+  return p.x_on ? p.x.q_all[p.x.rank] + ((size_t)(xstep & 1u) * p.x.Q + (size_t)p.x_row0) * D : p.out;
+}
 
 using ptx::treduce;
 
@@ -259,7 +268,7 @@ __device__ __forceinline__ void load_m_tmem(const Params& p, Meta* meta, int war
 //   ARRIVALS     mbarrier arrivals per published track (warps per track)
 template <int ARRIVALS, bool POOL_SMEM>
 __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw, int lane, int units, long long first0,
-                                            long long stride) {
+                                            long long stride, float* out_local, uint32_t xstep) {
   Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
   const uint32_t tmem = meta->tmem_base;
   const uint32_t lane_base = tmem + ((uint32_t)(hw * 32) << 16);
@@ -354,7 +363,7 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
       if (t < cnt) {                                      // warp-uniform
         const int track = meta->slot_track[buf][t];
         const float f = meta->fscale[buf][t] * ms_inv;
-        float* o = p.out + (size_t)track * D + ch;
+        float* o = out_local + (size_t)track * D + ch;
         float p0, p1;
         if constexpr (POOL_SMEM) {
           p0 = pool[t * D + ch];
@@ -363,8 +372,18 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
           p0 = __ldcg(o);
           p1 = __ldcg(o + 128);
         }
-        o[0] = fmaf(f, __uint_as_float(d0[t]), p0);
-        o[128] = fmaf(f, __uint_as_float(d1[t]), p1);
+        const float v0 = fmaf(f, __uint_as_float(d0[t]), p0), v1 = fmaf(f, __uint_as_float(d1[t]), p1);
+        o[0] = v0;
+        o[128] = v1;
+        if (p.x_on) {                                     // the same row into every peer's buffer (NVLink stores)
+          const size_t off = ((size_t)(xstep & 1u) * p.x.Q + (size_t)p.x_row0 + (size_t)track) * D + ch;
+          for (int r = 0; r < p.x.world; ++r) {
+            if (r == p.x.rank) continue;
+            float* po = p.x.q_all[r] + off;
+            po[0] = v0;
+            po[128] = v1;
+          }
+        }
       }
     }
     __syncwarp();
@@ -402,6 +421,11 @@ __device__ __forceinline__ void fused_teardown(uint8_t* fz, int warp, int helper
   if (warp == helper0) ptx::tmem_dealloc(reinterpret_cast<Meta*>(fz + OFF_META)->tmem_base, 512);
 }
 
+// a rank that has no tracks in a step still tells the others that its (empty) share of the descriptors is complete
+__global__ void signal_only_kernel(const xchg::Exchange x) {
+  xchg::signal_all(x, xchg::KIND_Q, xchg::current_step(x));
+}
+
 // ================================================================================================
 // Short tracks (up to TR = 4 / 10 / 16 frames): one producer WARP per track.
 // ================================================================================================
@@ -434,6 +458,8 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(ptx::FULL_MASK, threadIdx.x >> 5, 0);
   Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
+  const uint32_t xstep = p.x_on ? xchg::current_step(p.x) : 0u;
+  float* const out_local = local_out(p, xstep);
 
   const long long stride = (long long)gridDim.x * NW;
   const long long first0 = (long long)blockIdx.x * NW;
@@ -509,7 +535,7 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
   if (warp >= NW) {
     ptx::reg_dec<Cfg<TR>::REGS_H>();
     load_m_tmem<SEAM_AGG_INIT_WARPS(NW + HELPER_WARPS), 2>(p, meta, SEAM_AGG_INIT_WARPS(NW + HELPER_WARPS) == HELPER_WARPS ? warp - NW : warp, lane);
-    helper_role<1, true>(p, fz, warp - NW, lane, NW, first0, stride);
+    helper_role<1, true>(p, fz, warp - NW, lane, NW, first0, stride, out_local, xstep);
   } else {
     ptx::reg_inc<Cfg<TR>::REGS_P>();
     if (warp == 0) SEAM_TL2(p, 2);
@@ -692,6 +718,7 @@ __global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1) aggregat
     }
   }
   fused_teardown(fz, warp, NW);
+  if (p.x_on && p.x_last) xchg::signal_all(p.x, xchg::KIND_Q, xstep);
   if (warp == 0) SEAM_TL(p, 7);
 }
 
@@ -738,6 +765,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(ptx::FULL_MASK, threadIdx.x >> 5, 0);
   Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
+  const uint32_t xstep = p.x_on ? xchg::current_step(p.x) : 0u;
+  float* const out_local = local_out(p, xstep);
   const long long stride = (long long)gridDim.x * GROUPS_PER_CTA;
   const long long first0 = (long long)blockIdx.x * GROUPS_PER_CTA;
 
@@ -803,7 +832,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
   if (warp >= GWARPS) {
     ptx::reg_dec<GREGS_H>();
     load_m_tmem<SEAM_AGG_INIT_WARPS(GWARPS + HELPER_WARPS), 2>(p, meta, SEAM_AGG_INIT_WARPS(GWARPS + HELPER_WARPS) == HELPER_WARPS ? warp - GWARPS : warp, lane);
-    helper_role<GW, false>(p, fz, warp - GWARPS, lane, GROUPS_PER_CTA, first0, stride);
+    helper_role<GW, false>(p, fz, warp - GWARPS, lane, GROUPS_PER_CTA, first0, stride, out_local, xstep);
   } else {
     ptx::reg_inc<GREGS_P>();
     const float* fold = p.fold;
@@ -970,7 +999,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
             po.x += fmaf(qsum, wbg.x, bw.x);
             po.y += fmaf(qsum, wbg.y, bw.y);
           }
-          *reinterpret_cast<float2*>(p.out + (size_t)track * D + c) = po;
+          *reinterpret_cast<float2*>(out_local + (size_t)track * D + c) = po;
           store_r2(rt, pos, c, rr.x, rr.y, scale);
         }
         if (wg == 0 && lane == 0) {
@@ -985,6 +1014,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
     }
   }
   fused_teardown(fz, warp, GWARPS);
+  if (p.x_on && p.x_last) xchg::signal_all(p.x, xchg::KIND_Q, xstep);
 }
 
 }  // namespace aggf

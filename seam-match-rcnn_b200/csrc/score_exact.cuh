@@ -9,6 +9,7 @@
 #include <climits>
 #include <cstdint>
 #include <cuda_fp16.h>
+#include "exchange.cuh"
 #include "fold.cuh"
 #include "sm100_ptx.cuh"
 #include "warp_sort.cuh"
@@ -116,16 +117,22 @@ __global__ void __launch_bounds__(256) prep_gallery_kernel(const float* __restri
 
 // ---------------------------------------------------------------- query preparation
 // warp per query: a = -2 dw (.) q as fp16, rq = dw . q^2, ||a||, threshold reset
-__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int Q,
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* q, int Q,
                                                            const float* __restrict__ fold, __half* __restrict__ a16,
                                                            float* __restrict__ rq, float* __restrict__ anorm,
                                                            uint32_t* __restrict__ thr_global,
                                                            uint32_t* __restrict__ rowcnt, int nlists,
                                                            float* __restrict__ gmax,
                                                            uint32_t* __restrict__ rowflag,
-                                                           int32_t* __restrict__ counters) {
+                                                           int32_t* __restrict__ counters, const int x_on,
+                                                           const xchg::Exchange xc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + warp;
+  if (x_on) {   // sharded search: the queries are the descriptors every rank has written into this rank's q_all
+    const uint32_t step = xchg::current_step(xc);
+    xchg::wait_all(xc, xchg::KIND_Q, step);
+    q = xc.q_all[xc.rank] + (size_t)(step & 1u) * xc.Q * 256;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     counters[0] = 0;   // rows needing the exhaustive pass
     counters[1] = 0;   // fp16 overflow among the queries
@@ -181,7 +188,35 @@ struct RescoreParams {
   int32_t* out_idx;
   int32_t* counters;      // [0] number of uncertified rows, [1] query overflow flag
   int32_t* fallback_rows; // (Q)
+  int x_on;               // sharded search: queries from the exchange's q_all, lists to the queries' owners
+  xchg::Exchange x;
 };
+
+// Where a query's top-k row goes.  Single GPU: row qi of the caller's (Q,k) outputs.  Sharded search: slot
+// `rank` of the list buffer of the rank that owns the query (it merges the shards' lists); the score is a
+// function of the margin and is not exchanged.
+struct TopkDest {
+  float* score;
+  float* margin;
+  int32_t* idx;
+};
+__device__ __forceinline__ TopkDest topk_dest(int x_on, const xchg::Exchange& x, uint32_t step, int qi, int k,
+                                              float* out_score, float* out_margin, int32_t* out_idx) {
+  TopkDest d;
+  if (!x_on) {
+    const size_t o = (size_t)qi * k;
+    d.score = out_score + o;
+    d.margin = out_margin + o;
+    d.idx = out_idx + o;
+  } else {
+    const int ow = xchg::owner_of(x, qi);
+    const size_t o = ((((size_t)(step & 1u) * x.world + x.rank) * x.own_max) + (size_t)(qi - x.q_lo[ow])) * k;
+    d.score = nullptr;
+    d.margin = x.list_margin[ow] + o;
+    d.idx = x.list_idx[ow] + o;
+  }
+  return d;
+}
 
 // warp per query.
 //  1. streams the row's candidate sub-lists (everything the tensor-core pass saw above the
@@ -227,6 +262,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * 8 + warp;
   if (qi >= p.Q) return;
+  const uint32_t xstep = p.x_on ? xchg::current_step(p.x) : 0u;
+  const float* qbase = p.x_on ? p.x.q_all[p.x.rank] + (size_t)(xstep & 1u) * p.x.Q * 256 : p.q;
   const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
   bool certified = !overflow && p.rowflag[qi] == 0;
   const float tau = ptx::ordered_to_float(p.thr_global[qi]);
@@ -390,7 +427,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   if (p.G > 32 && (smask >> 31)) certified = false;       // S fills the window
   const int ns = __popc(smask);                           // S is a prefix of the sorted lanes
 
-  const Slice qs = load_slice(p.q + (size_t)qi * 256, lane);
+  const Slice qs = load_slice(qbase + (size_t)qi * 256, lane);
   const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
   const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
   const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
@@ -426,14 +463,13 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   if (__any_sync(ptx::FULL_MASK, violated)) certified = false;
   wsort::sort32_rank2(d, id, lane);
   if (lane < p.k) {
-    const size_t o = (size_t)qi * p.k + lane;
+    const TopkDest dst = topk_dest(p.x_on, p.x, xstep, qi, p.k, p.out_score, p.out_margin, p.out_idx);
     const bool ok = id != INT_MAX;
     // softmax(l0, l1)[1] depends on the logits only through d = l1 - l0 (the larger logit is
     // subtracted exactly), so it is formed after the sort: bit-identical to softmax1(l0, l1)
-    const float sc = softmax1(0.f, d);
-    p.out_score[o] = ok ? sc : 0.f;
-    p.out_margin[o] = d;
-    p.out_idx[o] = ok ? id + p.index_offset : -1;
+    if (dst.score) dst.score[lane] = ok ? softmax1(0.f, d) : 0.f;
+    dst.margin[lane] = d;
+    dst.idx[lane] = ok ? id + p.index_offset : -1;
   }
   if (!certified && lane == 0) {
     const int slot = atomicAdd(p.counters, 1);
@@ -452,6 +488,8 @@ struct ExactParams {
   float* out_score;
   float* out_margin;
   int32_t* out_idx;
+  int x_on;               // sharded search: see RescoreParams; this is the step's last list-writing kernel: it signals
+  xchg::Exchange x;
 };
 
 // CTA (8 warps) per row: each warp scans every 8th gallery item keeping a sorted best-32 in
@@ -461,12 +499,14 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
   __shared__ int si[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrows = p.count ? *p.count : p.Q;
+  const uint32_t xstep = p.x_on ? xchg::current_step(p.x) : 0u;
+  const float* qbase = p.x_on ? p.x.q_all[p.x.rank] + (size_t)(xstep & 1u) * p.x.Q * 256 : p.q;
   const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
   const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
   const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
   for (int e = blockIdx.x; e < nrows; e += gridDim.x) {
     const int qi = p.count ? p.rows[e] : e;
-    const Slice qs = load_slice(p.q + (size_t)qi * 256, lane);
+    const Slice qs = load_slice(qbase + (size_t)qi * 256, lane);
     float cd = -INFINITY;
     int cidx = INT_MAX;
     for (int j = warp; j < p.G; j += 8) {
@@ -512,14 +552,18 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
         if (lane == c) my_sc = softmax1(l0, l1);
       }
       if (lane < p.k) {
-        const size_t o = (size_t)qi * p.k + lane;
+        const TopkDest dst = topk_dest(p.x_on, p.x, xstep, qi, p.k, p.out_score, p.out_margin, p.out_idx);
         const bool ok = cidx != INT_MAX;
-        p.out_score[o] = ok ? my_sc : 0.f;
-        p.out_margin[o] = cd;
-        p.out_idx[o] = ok ? cidx + p.index_offset : -1;
+        if (dst.score) dst.score[lane] = ok ? my_sc : 0.f;
+        dst.margin[lane] = cd;
+        dst.idx[lane] = ok ? cidx + p.index_offset : -1;
       }
     }
     __syncthreads();
+  }
+  if (p.x_on) {          // every list row of this step (re-score kernel before, this one now) is on its way
+    __syncthreads();
+    xchg::signal_all(p.x, xchg::KIND_L, xstep);
   }
 }
 
@@ -808,6 +852,84 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict
     out_score[o] = ok ? (scores ? s : softmax1(0.f, d)) : 0.f;
     out_margin[o] = ok ? d : -INFINITY;
     out_idx[o] = ok ? id : -1;
+  }
+}
+
+// Sharded merge: this rank merges the world per-shard lists of the queries it OWNS (they were written into its
+// list buffer by every rank's re-score kernels), writes the merged rows into the final (Q,k) buffers of every
+// rank when the exchange has them (else into the caller's (own,k) outputs), and -- as the last kernel of a step
+// -- waits for every rank's merged rows to have landed here and advances the step.
+__global__ void __launch_bounds__(256) merge_sharded_kernel(const xchg::Exchange x, float* __restrict__ out_score,
+                                                            float* __restrict__ out_margin,
+                                                            int32_t* __restrict__ out_idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t step = xchg::current_step(x);
+  xchg::wait_all(x, xchg::KIND_L, step);
+  const int own = x.q_lo[x.rank + 1] - x.q_lo[x.rank], k = x.k;
+  const int qo = blockIdx.x * 8 + warp;
+  if (qo < own) {
+    const float* margins = x.list_margin[x.rank] + (size_t)(step & 1u) * x.world * x.own_max * k;
+    const int32_t* idx = x.list_idx[x.rank] + (size_t)(step & 1u) * x.world * x.own_max * k;
+    float d = -INFINITY, s = 0.f;
+    int id = INT_MAX;
+    for (int n = 0; n < x.world; ++n) {
+      const size_t base = ((size_t)n * x.own_max + qo) * k;
+      const int e = n == 0 ? lane : 31 - lane;   // later lists reversed: worst first
+      float od = -INFINITY;
+      int oi = INT_MAX;
+      if (e < k) {
+        const int32_t ii = __ldcg(idx + base + e);
+        if (ii >= 0) {
+          od = __ldcg(margins + base + e);
+          oi = ii;
+        }
+      }
+      if (n == 0) {
+        d = od;
+        id = oi;
+      } else {
+        if (wsort::ranks_before(od, oi, d, id)) {
+          d = od;
+          id = oi;
+        }
+        wsort::merge32_rank(d, id, s, lane);
+      }
+    }
+    if (lane < k) {
+      const bool ok = id != INT_MAX;
+      const float sc = ok ? softmax1(0.f, d) : 0.f;
+      const float dm = ok ? d : -INFINITY;
+      const int ii = ok ? id : -1;
+      if (x.final_score[0]) {
+        const size_t o = (size_t)(x.q_lo[x.rank] + qo) * k + lane;
+        for (int r = 0; r < x.world; ++r) {
+          x.final_score[r][o] = sc;
+          x.final_margin[r][o] = dm;
+          x.final_idx[r][o] = ii;
+        }
+      } else {
+        const size_t o = (size_t)qo * k + lane;
+        out_score[o] = sc;
+        out_margin[o] = dm;
+        out_idx[o] = ii;
+      }
+    }
+  }
+  __syncthreads();
+  if (xchg::signal_all(x, xchg::KIND_F, step)) {       // thread 0 of the grid's last CTA
+    if (x.final_score[0]) {
+      for (int r = 0; r < x.world; ++r) {
+        const uint32_t* f = x.flags[x.rank] + xchg::KIND_F * xchg::MAX_WORLD + r;
+        uint64_t t0 = 0;
+        while ((int32_t)(xchg::ld_acquire_sys(f) - step) < 0) {
+          __nanosleep(100);
+          const uint64_t now = ptx::globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 10000000000ull) ptx::watchdog_trap(210u, (uint32_t)r, step);
+        }
+      }
+    }
+    *reinterpret_cast<volatile uint32_t*>(x.step) = step + 1u;
   }
 }
 

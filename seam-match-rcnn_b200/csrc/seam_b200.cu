@@ -134,9 +134,45 @@ static void launch_aggregate_group(const aggf::Params& p, int num_sms, cudaStrea
   aggf::aggregate_fused_group_kernel<GW><<<grid, aggf::GTHREADS, aggf::group_smem_bytes<GW>(), stream>>>(p);
 }
 
+static int import_exchange(seam_handle* h, const seam_exchange* x, xchg::Exchange* e, const char* who) {
+  if (!x) return fail(h, SEAM_ERR_BAD_ARG, "%s: exchange is null", who);
+  if (x->world < 1 || x->world > SEAM_MAX_WORLD || x->rank < 0 || x->rank >= x->world)
+    return fail(h, SEAM_ERR_BAD_ARG, "%s: world=%d rank=%d outside [1,%d]", who, x->world, x->rank, SEAM_MAX_WORLD);
+  if (x->Q < 0 || x->k < 1 || x->k > SEAM_MAX_K || x->own_max < 0)
+    return fail(h, SEAM_ERR_BAD_ARG, "%s: bad Q / k / own_max", who);
+  if (x->q_lo[0] != 0 || x->q_lo[x->world] != x->Q) return fail(h, SEAM_ERR_BAD_ARG, "%s: q_lo must run from 0 to Q", who);
+  if (!x->step || !x->done) return fail(h, SEAM_ERR_BAD_ARG, "%s: step / done are null", who);
+  memset(e, 0, sizeof(*e));
+  e->world = x->world;
+  e->rank = x->rank;
+  e->Q = x->Q;
+  e->k = x->k;
+  e->own_max = x->own_max;
+  const bool have_final = x->final_score[0] != nullptr;
+  for (int r = 0; r <= x->world; ++r) e->q_lo[r] = x->q_lo[r];
+  for (int r = 0; r < x->world; ++r) {
+    if (x->q_lo[r + 1] < x->q_lo[r] || x->q_lo[r + 1] - x->q_lo[r] > x->own_max)
+      return fail(h, SEAM_ERR_BAD_ARG, "%s: q_lo not monotone or ownership above own_max", who);
+    if (!x->q_all[r] || !x->list_margin[r] || !x->list_idx[r] || !x->flags[r])
+      return fail(h, SEAM_ERR_BAD_ARG, "%s: null buffer for rank %d", who, r);
+    if (have_final && (!x->final_score[r] || !x->final_margin[r] || !x->final_idx[r]))
+      return fail(h, SEAM_ERR_BAD_ARG, "%s: final buffers must be given for all ranks or none", who);
+    e->q_all[r] = x->q_all[r];
+    e->list_margin[r] = x->list_margin[r];
+    e->list_idx[r] = x->list_idx[r];
+    e->final_score[r] = have_final ? x->final_score[r] : nullptr;
+    e->final_margin[r] = have_final ? x->final_margin[r] : nullptr;
+    e->final_idx[r] = have_final ? x->final_idx[r] : nullptr;
+    e->flags[r] = x->flags[r];
+  }
+  e->step = x->step;
+  e->done = x->done;
+  return SEAM_OK;
+}
+
 extern "C" {
 
-int seam_abi_version(void) { return 1; }
+int seam_abi_version(void) { return 2; }
 
 int seam_create(seam_handle** out, int device) {
   if (!out) return fail(nullptr, SEAM_ERR_BAD_ARG, "seam_create: out is null");
@@ -313,48 +349,84 @@ size_t seam_aggregate_workspace_bytes(int Q) {
   return 256;   // the fused kernel keeps every intermediate on the SM
 }
 
+static int aggregate_impl(seam_handle* h, const xchg::Exchange* x, int row0, int last, const float* seq,
+                          const uint8_t* mask, const int32_t* lens, int Tmax, int Q, int64_t frame_stride,
+                          int64_t track_stride, float* out, float* att, cudaStream_t stream, const char* who) {
+  if (!h->have_aggregator) return fail(h, SEAM_ERR_STATE, "%s: weights not loaded", who);
+  if (Q < 0 || Tmax < 0) return fail(h, SEAM_ERR_BAD_ARG, "%s: negative size", who);
+  if (!x && Q == 0) return SEAM_OK;
+  if (!x && !out) return fail(h, SEAM_ERR_BAD_ARG, "%s: out is null", who);
+  if (Tmax > SEAM_MAX_T) return fail(h, SEAM_ERR_UNSUPPORTED, "%s: Tmax=%d exceeds %d", who, Tmax, SEAM_MAX_T);
+  DeviceGuard guard(h->device);
+  if (!x && Tmax == 0) {   // only the dummy row: every track is empty -> zero descriptors
+    SEAM_CUDA(h, cudaMemsetAsync(out, 0, (size_t)Q * 256 * 4, stream));
+    return SEAM_OK;
+  }
+  if (Q > 0 && Tmax > 0 && !seq) return fail(h, SEAM_ERR_BAD_ARG, "%s: null pointer", who);
+  if (!aligned16(seq) || (out && !aligned16(out)) || (frame_stride & 3) || (track_stride & 3))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "%s: seq/out must be 16-byte aligned, strides multiples of 4", who);
+  ProfileScope prof(h, SEAM_KERNEL_AGGREGATE, stream);
+  aggf::Params p;
+  memset(&p, 0, sizeof(p));
+  p.seq = seq;
+  p.mask = mask;
+  p.lens = lens;
+  p.Tmax = Tmax;
+  p.Q = Q;
+  p.frame_stride = frame_stride;
+  p.track_stride = track_stride;
+  p.fold = h->fold;
+  p.out = out;
+  p.att = att;
+  if (x) {
+    p.x_on = 1;
+    p.x_last = last;
+    p.x_row0 = row0;
+    p.x = *x;
+    // a rank without tracks in this call (or with empty tracks only: Tmax == 0) still has to take part in the
+    // protocol: one CTA, zero tracks / zero-length tracks, descriptors = 0
+    if (Tmax == 0) { p.Tmax = 1; p.lens = nullptr; p.mask = nullptr; p.seq = nullptr; p.Q = -Q; }
+  }
+  const int cap = h->dbg_agg_grid > 0 && h->dbg_agg_grid < h->num_sms ? h->dbg_agg_grid : h->num_sms;
+  if (p.Q < 0) return fail(h, SEAM_ERR_UNSUPPORTED, "%s: Tmax == 0 in the sharded search", who);
+  if (p.Q == 0) {
+    // nothing to aggregate on this rank: only the signal is needed
+    if (x && last) {
+      aggf::signal_only_kernel<<<1, 32, 0, stream>>>(p.x);
+      SEAM_LAUNCHED(h, "signal_only_kernel");
+    }
+    return SEAM_OK;
+  }
+  if (Tmax <= 4) launch_aggregate_warp<4>(p, cap, stream);
+  else if (Tmax <= 10) launch_aggregate_warp<10>(p, cap, stream);
+  else if (Tmax <= 16) launch_aggregate_warp<16>(p, cap, stream);
+  else if (Tmax <= 32) launch_aggregate_group<2>(p, cap, stream);   // two warps per track
+  else launch_aggregate_group<4>(p, cap, stream);                   // 33..64 frames: four warps per track
+  SEAM_LAUNCHED(h, "aggregate kernel");
+  return SEAM_OK;
+}
+
 int seam_aggregate(seam_handle* h, const float* seq, const uint8_t* mask, const int32_t* lens, int Tmax, int Q,
                    int64_t frame_stride, int64_t track_stride, float* out, float* att, void* workspace,
                    size_t workspace_bytes, void* stream_) {
   (void)workspace;
   (void)workspace_bytes;
   if (!h) return SEAM_ERR_BAD_ARG;
-  if (!h->have_aggregator) return fail(h, SEAM_ERR_STATE, "seam_aggregate: weights not loaded");
-  if (Q < 0 || Tmax < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: negative size");
-  if (Q == 0) return SEAM_OK;
-  if (!out) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: out is null");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DeviceGuard guard(h->device);
-  if (Tmax == 0) {   // only the dummy row: every track is empty -> zero descriptors
-    SEAM_CUDA(h, cudaMemsetAsync(out, 0, (size_t)Q * 256 * 4, stream));
-    return SEAM_OK;
-  }
-  if (Tmax > SEAM_MAX_T) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: Tmax=%d exceeds %d", Tmax, SEAM_MAX_T);
-  if (!seq) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate: null pointer");
-  if (!aligned16(seq) || !aligned16(out) || (frame_stride & 3) || (track_stride & 3))
-    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate: seq/out must be 16-byte aligned, strides multiples of 4");
-  {
-    ProfileScope prof(h, SEAM_KERNEL_AGGREGATE, stream);
-    aggf::Params p;
-    p.seq = seq;
-    p.mask = mask;
-    p.lens = lens;
-    p.Tmax = Tmax;
-    p.Q = Q;
-    p.frame_stride = frame_stride;
-    p.track_stride = track_stride;
-    p.fold = h->fold;
-    p.out = out;
-    p.att = att;
-    const int cap = h->dbg_agg_grid > 0 && h->dbg_agg_grid < h->num_sms ? h->dbg_agg_grid : h->num_sms;
-    if (Tmax <= 4) launch_aggregate_warp<4>(p, cap, stream);
-    else if (Tmax <= 10) launch_aggregate_warp<10>(p, cap, stream);
-    else if (Tmax <= 16) launch_aggregate_warp<16>(p, cap, stream);
-    else if (Tmax <= 32) launch_aggregate_group<2>(p, cap, stream);   // two warps per track
-    else launch_aggregate_group<4>(p, cap, stream);                   // 33..64 frames: four warps per track
-    SEAM_LAUNCHED(h, "aggregate kernel");
-  }
-  return SEAM_OK;
+  return aggregate_impl(h, nullptr, 0, 0, seq, mask, lens, Tmax, Q, frame_stride, track_stride, out, att,
+                        static_cast<cudaStream_t>(stream_), "seam_aggregate");
+}
+
+int seam_sharded_aggregate(seam_handle* h, const seam_exchange* x, const float* seq, const uint8_t* mask,
+                           const int32_t* lens, int Tmax, int Qlocal, int64_t frame_stride, int64_t track_stride,
+                           int row0, int last, float* att, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  xchg::Exchange e;
+  int rc = import_exchange(h, x, &e, "seam_sharded_aggregate");
+  if (rc != SEAM_OK) return rc;
+  if (row0 < 0 || Qlocal < 0 || row0 + Qlocal > x->Q)
+    return fail(h, SEAM_ERR_BAD_ARG, "seam_sharded_aggregate: rows [%d,%d) outside the %d queries", row0, row0 + Qlocal, x->Q);
+  return aggregate_impl(h, &e, row0, last ? 1 : 0, seq, mask, lens, Tmax, Qlocal, frame_stride, track_stride, nullptr, att,
+                        static_cast<cudaStream_t>(stream_), "seam_sharded_aggregate");
 }
 
 size_t seam_nlb_workspace_bytes(int B, int T) {
@@ -606,18 +678,25 @@ static int encode_map_fp16_rows(seam_handle* h, CUtensorMap* map, const void* ba
   return SEAM_OK;
 }
 
-int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const void* g16, const float* cg,
-                    const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin,
-                    int32_t* out_idx, int32_t* stats, void* workspace, size_t workspace_bytes, void* stream_) {
-  if (!h) return SEAM_ERR_BAD_ARG;
+static int score_topk_impl(seam_handle* h, const xchg::Exchange* x, const float* q, int Q, const float* g,
+                           const void* g16, const float* cg, const float* gstat, int G, int index_offset, int k,
+                           float* out_score, float* out_margin, int32_t* out_idx, int32_t* stats, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
   if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_score_topk: scorer weights not loaded");
   if (Q < 0 || G < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_topk: negative size");
   if (k < 1 || k > SEAM_MAX_K) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_topk: k=%d outside [1,%d]", k, SEAM_MAX_K);
-  if (Q == 0) return SEAM_OK;
-  if (!out_score || !out_margin || !out_idx) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_topk: null output");
+  if (Q == 0 && !x) return SEAM_OK;
+  if (!x && (!out_score || !out_margin || !out_idx)) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_topk: null output");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DeviceGuard guard(h->device);
   if (stats) SEAM_CUDA(h, cudaMemsetAsync(stats, 0, 16, stream));
+  if (x && (Q == 0 || G == 0))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_sharded_score_topk: every rank needs queries and a non-empty gallery shard");
+  const int x_on = x ? 1 : 0;
+  xchg::Exchange xe;
+  memset(&xe, 0, sizeof(xe));
+  if (x) xe = *x;
+  if (x) q = x->q_all[x->rank];      // alignment checks below; the kernels pick the step's parity half themselves
   if (G == 0) {
     const size_t n = (size_t)Q * k;
     fill_empty_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out_score, out_margin, out_idx, n);
@@ -649,7 +728,7 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   {
     ProfileScope prof(h, SEAM_KERNEL_PREP_QUERIES, stream);
     exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt,
-                                                               s.P * score::NQ, gmax, rowflag, counters);
+                                                               s.P * score::NQ, gmax, rowflag, counters, x_on, xe);
     SEAM_LAUNCHED(h, "prep_queries_kernel");
   }
 
@@ -721,6 +800,8 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   rp.out_idx = out_idx;
   rp.counters = counters;
   rp.fallback_rows = frows;
+  rp.x_on = x_on;
+  rp.x = xe;
   {
     ProfileScope prof(h, SEAM_KERNEL_RESCORE, stream);
     exact::rescore_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(rp);
@@ -740,12 +821,49 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
   ep.out_score = out_score;
   ep.out_margin = out_margin;
   ep.out_idx = out_idx;
+  ep.x_on = x_on;
+  ep.x = xe;
   {
     ProfileScope prof(h, SEAM_KERNEL_EXACT, stream);
     exact::exact_topk_kernel<<<2 * h->num_sms, 256, 0, stream>>>(ep);
     SEAM_LAUNCHED(h, "exact_topk_kernel");
   }
   if (stats) SEAM_CUDA(h, cudaMemcpyAsync(stats, counters, 4, cudaMemcpyDeviceToDevice, stream));
+  return SEAM_OK;
+}
+
+int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const void* g16, const float* cg,
+                    const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin,
+                    int32_t* out_idx, int32_t* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  return score_topk_impl(h, nullptr, q, Q, g, g16, cg, gstat, G, index_offset, k, out_score, out_margin, out_idx, stats,
+                         workspace, workspace_bytes, stream_);
+}
+
+int seam_sharded_score_topk(seam_handle* h, const seam_exchange* x, const float* g, const void* g16, const float* cg,
+                            const float* gstat, int G, int index_offset, int32_t* stats, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  xchg::Exchange e;
+  int rc = import_exchange(h, x, &e, "seam_sharded_score_topk");
+  if (rc != SEAM_OK) return rc;
+  return score_topk_impl(h, &e, nullptr, x->Q, g, g16, cg, gstat, G, index_offset, x->k, nullptr, nullptr, nullptr, stats,
+                         workspace, workspace_bytes, stream_);
+}
+
+int seam_sharded_merge(seam_handle* h, const seam_exchange* x, float* out_score, float* out_margin, int32_t* out_idx,
+                       void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  xchg::Exchange e;
+  int rc = import_exchange(h, x, &e, "seam_sharded_merge");
+  if (rc != SEAM_OK) return rc;
+  if (!e.final_score[0] && (!out_score || !out_margin || !out_idx))
+    return fail(h, SEAM_ERR_BAD_ARG, "seam_sharded_merge: no final buffers in the exchange and null outputs");
+  DeviceGuard guard(h->device);
+  const int own = e.q_lo[e.rank + 1] - e.q_lo[e.rank];
+  const int grid = own > 0 ? (own + 7) / 8 : 1;
+  exact::merge_sharded_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(e, out_score, out_margin, out_idx);
+  SEAM_LAUNCHED(h, "merge_sharded_kernel");
   return SEAM_OK;
 }
 
@@ -826,8 +944,10 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
   float* hi = lo + Q;
   float* dtarget = hi + Q;
 
+  xchg::Exchange no_x;
+  memset(&no_x, 0, sizeof(no_x));
   exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt, nlists, gmax,
-                                                             rowflag, counters);
+                                                             rowflag, counters, 0, no_x);
   SEAM_LAUNCHED(h, "prep_queries_kernel");
   exact::rank_prep_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, g, target, h->fold, rq, anorm, gstat, lo, hi, dtarget,
                                                           above, nlists);

@@ -5,6 +5,7 @@ the hot path runs in the hand-written kernels behind ``libseam_b200.so``.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, Mapping, Optional, Tuple
@@ -15,6 +16,13 @@ from . import _lib
 from ._lib import SeamError, SeamWeights, WEIGHT_KEYS
 
 D_MODEL = 256
+# shapes of the reference's hot-path parameters (TemporalAggregationNLB().state_dict())
+WEIGHT_SHAPES = {
+    "theta_w": (128, 256, 1), "theta_b": (128,), "phi_w": (128, 256, 1), "phi_b": (128,),
+    "g_w": (128, 256, 1), "g_b": (128,), "W_w": (256, 128, 1), "W_b": (256,),
+    "concat_w": (1, 256, 1, 1), "att_w": (1, 256), "att_b": (1,), "last_w": (2, 256), "last_b": (2,),
+}
+SCORE_WS_LIMIT = 2 << 30      # bytes of scorer workspace above which score_topk works through the queries in slabs
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -35,6 +43,7 @@ class PreparedGallery:
     cg: torch.Tensor
     gstat: torch.Tensor
     index_offset: int = 0
+    scorer_epoch: int = -1      # the engine's scorer epoch cg / g16 were prepared under (cg = dw . g^2 depends on `last`)
 
     @property
     def G(self) -> int:
@@ -60,6 +69,9 @@ class SeamEngine:
         self._ws: Dict[str, torch.Tensor] = {}
         self._weights_key = None
         self._weight_refs = None
+        self._last = None            # (last.weight, last.bias) currently folded into the handle
+        self.weights_epoch = 0       # bumped by every load_weights / load_scorer
+        self.scorer_epoch = 0        # bumped whenever `last` is (re)loaded: prepared galleries are tied to it
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -130,11 +142,17 @@ class SeamEngine:
             k = prefix + key
             if k not in state:
                 raise KeyError(f"state_dict is missing '{k}'")
-            tensors[field] = self._f32(state[k].detach(), k)
+            t = state[k].detach()
+            if tuple(t.shape) != WEIGHT_SHAPES[field]:      # the fold kernels index these buffers by the reference's shapes
+                raise ValueError(f"'{k}' has shape {tuple(t.shape)}, expected {WEIGHT_SHAPES[field]} "
+                                 "(TemporalAggregationNLB with d_model=256, inter_channels=128)")
+            tensors[field] = self._f32(t, k)
         w = SeamWeights(**{f: tensors[f].data_ptr() for f in SeamWeights.FIELDS})
         self._check(self._lib.seam_load_weights(self._h, C.byref(w), self._stream()))
         self._weight_refs = tensors   # keep alive until the fold kernels have run
-        self.weights_epoch = getattr(self, "weights_epoch", 0) + 1
+        self._last = (tensors["last_w"], tensors["last_b"])
+        self.weights_epoch += 1
+        self.scorer_epoch += 1
 
     def load_scorer(self, last_w: torch.Tensor, last_b: torch.Tensor) -> None:
         """Only ``last`` (e.g. ``match_predictor.last`` for the per-frame scorers)."""
@@ -143,7 +161,22 @@ class SeamEngine:
             raise ValueError("last.weight must be (2,256) and last.bias (2,)")
         self._check(self._lib.seam_load_scorer(self._h, lw.data_ptr(), lb.data_ptr(), self._stream()))
         self._weight_refs = (lw, lb)
-        self.weights_epoch = getattr(self, "weights_epoch", 0) + 1
+        self._last = (lw, lb)
+        self.weights_epoch += 1
+        self.scorer_epoch += 1
+
+    @contextlib.contextmanager
+    def scorer(self, last_w: torch.Tensor, last_b: torch.Tensor):
+        """Temporarily score with another ``last`` (e.g. ``match_predictor.last`` for the per-frame rows of the
+        eval script) and put the previous scorer back on exit, so that callers sharing this engine -- modules,
+        ShardedRetriever, prepared galleries -- are not left with somebody else's weights."""
+        prev = self._last
+        self.load_scorer(last_w, last_b)
+        try:
+            yield self
+        finally:
+            if prev is not None:
+                self.load_scorer(*prev)
 
     # ------------------------------------------------------------------ (a) aggregation
     def _out(self, out: Optional[torch.Tensor], shape, dtype, name: str) -> torch.Tensor:
@@ -187,6 +220,67 @@ class SeamEngine:
                                              ws.data_ptr(), ws.numel(), self._stream()))
         return (out, att) if getatt else out
 
+    # ------------------------------------------------------------------ gallery-sharded search (exchange in the kernels)
+    def _tracks(self, seq, mask, lens):
+        """Argument normalisation shared by aggregate / sharded_aggregate."""
+        if seq.dim() != 3 or seq.shape[2] != D_MODEL:
+            raise ValueError(f"x3_1_seq must be (1+Tmax, Q, 256), got {tuple(seq.shape)}")
+        if seq.device != self.device or seq.dtype != torch.float32:
+            seq = seq.to(device=self.device, dtype=torch.float32)
+        if seq.stride(2) != 1 or seq.stride(0) % 4 or seq.stride(1) % 4:
+            seq = seq.contiguous()
+        Tmax, Q = seq.shape[0] - 1, seq.shape[1]
+        if Tmax > _lib.SEAM_MAX_T:
+            raise SeamError(2, f"Tmax={Tmax} exceeds the supported {_lib.SEAM_MAX_T} frames per track")
+        m8 = None
+        if mask is not None:
+            if tuple(mask.shape) != (Q, 1 + Tmax):
+                raise ValueError(f"x3_1_mask must be (Q, 1+Tmax)={Q, 1 + Tmax}, got {tuple(mask.shape)}")
+            m8 = mask.to(device=self.device, dtype=torch.bool).contiguous().view(torch.uint8)
+        l32 = lens.to(device=self.device, dtype=torch.int32).contiguous() if lens is not None else None
+        return seq, m8, l32, Tmax, Q
+
+    def sharded_aggregate(self, x, seq: torch.Tensor, mask=None, lens=None, row0: Optional[int] = None,
+                          last: bool = True, getatt: bool = False):
+        """This rank's tracks (queries ``row0 .. row0+Qlocal`` of the step, default: the rows it owns) -> their
+        descriptors, stored by the kernel into EVERY rank's descriptor buffer (``x``: a ``retrieval.PeerExchange``).
+        ``last``: these are the rank's last tracks of the step (the other ranks are told it is complete)."""
+        seq, m8, l32, Tmax, Q = self._tracks(seq, mask, lens)
+        row0 = x.q_lo[x.rank] if row0 is None else int(row0)
+        att = torch.empty((Q, Tmax), dtype=torch.float32, device=self.device) if getatt else None
+        self._check(self._lib.seam_sharded_aggregate(self._h, C.byref(x.struct), seq.data_ptr() if Q else 0, _ptr(m8),
+                                                     _ptr(l32), Tmax, Q, seq.stride(0), seq.stride(1), row0,
+                                                     1 if last else 0, _ptr(att), self._stream()))
+        return att
+
+    def sharded_score_topk(self, x, gallery: PreparedGallery, return_stats: bool = False):
+        """All Q queries (once every rank's descriptors have landed here) against this rank's gallery shard; each
+        query's top-k row is stored into the list buffer of the rank that owns the query."""
+        gallery = self._fresh(gallery)
+        stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        nbytes = int(self._lib.seam_score_workspace_bytes(self._h, x.Q, gallery.G, x.k))
+        ws = self._workspace("score", nbytes)
+        self._check(self._lib.seam_sharded_score_topk(self._h, C.byref(x.struct), gallery.g.data_ptr(),
+                                                      gallery.g16.data_ptr(), gallery.cg.data_ptr(),
+                                                      gallery.gstat.data_ptr(), gallery.G, int(gallery.index_offset),
+                                                      stats.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+        return stats if return_stats else None
+
+    def sharded_merge(self, x):
+        """Merge the per-shard lists of the queries this rank owns and end the step.  Returns
+        ``(scores, margins, idx)``: the complete ``(Q,k)`` result on every rank when the exchange replicates it
+        (views of its final buffers, valid until the next step's merge), else this rank's ``(own,k)`` rows."""
+        if x.replicate:
+            self._check(self._lib.seam_sharded_merge(self._h, C.byref(x.struct), None, None, None, self._stream()))
+            return x.final
+        own = x.q_lo[x.rank + 1] - x.q_lo[x.rank]
+        sc = torch.empty((own, x.k), dtype=torch.float32, device=self.device)
+        mg = torch.empty((own, x.k), dtype=torch.float32, device=self.device)
+        ix = torch.empty((own, x.k), dtype=torch.int32, device=self.device)
+        self._check(self._lib.seam_sharded_merge(self._h, C.byref(x.struct), sc.data_ptr(), mg.data_ptr(), ix.data_ptr(),
+                                                 self._stream()))
+        return sc, mg, ix
+
     def nlb_forward(self, x: torch.Tensor) -> torch.Tensor:
         """NONLocalBlock1D.forward (models/nlb.py:66-101): (B,256,T) -> (B,256,T)."""
         if x.dim() != 3 or x.shape[1] != D_MODEL:
@@ -213,7 +307,18 @@ class SeamEngine:
         gstat = torch.empty((4,), dtype=torch.float32, device=self.device)
         self._check(self._lib.seam_prepare_gallery(self._h, g.data_ptr(), G, g16.data_ptr(), cg.data_ptr(),
                                                    gstat.data_ptr(), self._stream()))
-        return PreparedGallery(g=g, g16=g16, cg=cg, gstat=gstat, index_offset=index_offset)
+        return PreparedGallery(g=g, g16=g16, cg=cg, gstat=gstat, index_offset=index_offset,
+                               scorer_epoch=self.scorer_epoch)
+
+    def _fresh(self, gallery: PreparedGallery) -> PreparedGallery:
+        """A gallery prepared under another scorer (its cg = dw . g^2 and overflow statistics are stale after
+        load_weights / load_scorer) is prepared again in place: one pass over its fp32 rows."""
+        if gallery.scorer_epoch != self.scorer_epoch:
+            G = gallery.G
+            self._check(self._lib.seam_prepare_gallery(self._h, gallery.g.data_ptr(), G, gallery.g16.data_ptr(),
+                                                       gallery.cg.data_ptr(), gallery.gstat.data_ptr(), self._stream()))
+            gallery.scorer_epoch = self.scorer_epoch
+        return gallery
 
     def score_topk(self, q: torch.Tensor, gallery: PreparedGallery, k: int,
                    return_stats: bool = False, out=None):
@@ -222,6 +327,7 @@ class SeamEngine:
         if q.dim() != 2 or q.shape[1] != D_MODEL:
             raise ValueError(f"queries must be (Q,256), got {tuple(q.shape)}")
         q = self._f32(q, "queries")
+        gallery = self._fresh(gallery)
         Q, G = q.shape[0], gallery.G
         k = int(k)
         o = out if out is not None else (None, None, None)
@@ -229,13 +335,25 @@ class SeamEngine:
         mg = self._out(o[1], (Q, k), torch.float32, "score_topk margins")
         ix = self._out(o[2], (Q, k), torch.int32, "score_topk idx")
         stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
-        nbytes = int(self._lib.seam_score_workspace_bytes(self._h, Q, G, k))
-        ws = self._workspace("score", nbytes)
-        self._check(self._lib.seam_score_topk(self._h, q.data_ptr(), Q, gallery.g.data_ptr(),
-                                              gallery.g16.data_ptr(), gallery.cg.data_ptr(),
-                                              gallery.gstat.data_ptr(), G, int(gallery.index_offset), k,
-                                              sc.data_ptr(), mg.data_ptr(), ix.data_ptr(), stats.data_ptr(),
-                                              ws.data_ptr(), ws.numel(), self._stream()))
+        # The candidate lists take 12-96 KB per query row: very large evaluations are worked through in slabs of
+        # queries that reuse one bounded workspace (results do not depend on the slab size)
+        slab = Q
+        while slab > 1024 and int(self._lib.seam_score_workspace_bytes(self._h, slab, G, k)) > SCORE_WS_LIMIT:
+            slab = (slab + 1) // 2
+        for lo in range(0, max(Q, 1), max(slab, 1)):
+            hi = min(Q, lo + slab)
+            n = hi - lo
+            nbytes = int(self._lib.seam_score_workspace_bytes(self._h, n, G, k))
+            ws = self._workspace("score", nbytes)
+            st = stats if slab == Q else torch.zeros((4,), dtype=torch.int32, device=self.device)
+            self._check(self._lib.seam_score_topk(self._h, q[lo:hi].data_ptr() if n else 0, n, gallery.g.data_ptr(),
+                                                  gallery.g16.data_ptr(), gallery.cg.data_ptr(),
+                                                  gallery.gstat.data_ptr(), G, int(gallery.index_offset), k,
+                                                  sc[lo:hi].data_ptr() if n else 0, mg[lo:hi].data_ptr() if n else 0,
+                                                  ix[lo:hi].data_ptr() if n else 0, st.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), self._stream()))
+            if st is not stats:
+                stats += st
         if return_stats:
             return sc, mg, ix, stats
         return sc, mg, ix
@@ -264,6 +382,8 @@ class SeamEngine:
         the same integers.  Returns (rank int32 (Q,), target margin fp32 (Q,)[, stats])."""
         q = self._f32(q, "queries")
         prepared = isinstance(g, PreparedGallery)
+        if prepared:
+            g = self._fresh(g)
         gm = g.g if prepared else self._f32(g, "gallery")
         t32 = target.to(device=self.device, dtype=torch.int32).contiguous()
         Q, G = q.shape[0], gm.shape[0]

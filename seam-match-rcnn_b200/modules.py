@@ -26,6 +26,16 @@ class _EngineMixin:
     """Lazily creates a SeamEngine on the module's device and keeps its folded weights in
     sync with the module's parameters."""
 
+    _TRANSIENT = ("_seam_engine", "_seam_key", "_seam_epoch", "_gallery_cache")
+
+    def __getstate__(self):
+        # the engine wraps a ctypes handle (not picklable, not copyable): copy.deepcopy(model), pickle and
+        # torch.save(model) drop it and the copy re-creates its own on first use
+        state = dict(super().__getstate__())
+        for k in self._TRANSIENT:
+            state.pop(k, None)
+        return state
+
     def _engine_for(self, device: torch.device) -> SeamEngine:
         device = torch.device(device)
         if device.type != "cuda":
@@ -53,7 +63,7 @@ class _EngineMixin:
             self.__dict__["_seam_epoch"] = getattr(eng, "weights_epoch", 0)
 
 
-class NONLocalBlock1D(nn.Module, _EngineMixin):
+class NONLocalBlock1D(_EngineMixin, nn.Module):
     """Concatenation-form non-local block, models/nlb.py:5-101 as instantiated at
     models/match_head.py:87.  Only that instantiation is supported."""
 
@@ -96,7 +106,7 @@ class NONLocalBlock1D(nn.Module, _EngineMixin):
         return eng.nlb_forward(x)
 
 
-class MatchPredictor(nn.Module, _EngineMixin):
+class MatchPredictor(_EngineMixin, nn.Module):
     """models/match_head.py:47-76."""
 
     def __init__(self):
@@ -130,13 +140,17 @@ class MatchPredictor(nn.Module, _EngineMixin):
         self._sync_weights(eng)
         return eng.score_dense(q, g)
 
-    @torch.no_grad()
     def forward(self, x, types):
+        """``(x3, x5)`` as models/match_head.py:66-76.  The conv tower runs under autograd as in the reference
+        (``x3`` carries its graph); the pair scorer runs in the CUDA kernels without autograd history, so ``x5``
+        is detached -- training through the scorer is SURVEY.md section 8(f4).  Raises above 64M pairs
+        (``DENSE_PAIR_LIMIT``) instead of materialising x4 = (Q,G,256)."""
         x3 = self.embed(x)
         types = types.to(x3.device)
-        x3_1 = x3[types == 0]
-        x3_2 = x3[types == 1]
-        x5 = self._dense_logits(x3_1, x3_2)          # (Q,G,2): match_head.py:70-74
+        with torch.no_grad():
+            x3_1 = x3[types == 0]
+            x3_2 = x3[types == 1]
+            x5 = self._dense_logits(x3_1, x3_2)      # (Q,G,2): match_head.py:70-74
         return x3, x5
 
 
@@ -195,16 +209,25 @@ class TemporalAggregationNLB(MatchPredictor):
         lens = (first - 1).clamp(min=0).tolist()
         return [att[i, :n].unsqueeze(1) for i, n in enumerate(lens)]
 
-    @torch.no_grad()
     def forward(self, x, types, ids, x3_1_seq=None, x3_1_mask=None, x3_2=None, getatt=False):
-        attention_scores = None
-        if x3_1_seq is None:
-            x3 = self.embed(x)
+        """Same signature and return tuple as models/match_head.py:90-169.  Limits (errors, not fallbacks):
+        tracks of at most 64 frames (``SEAM_MAX_T``), x5 for at most 64M pairs (``DENSE_PAIR_LIMIT``; use
+        ``score_topk`` beyond).  The conv tower of the x-branch runs under autograd (``x3_2`` keeps its graph);
+        aggregation and scorer outputs are detached (inference kernels)."""
+        x3_1 = x3_1_ids = None
+        if x3_1_seq is None:                                   # x-branch: match_head.py:92-111
+            x3 = self.embed(x)                                 # under autograd, as in the reference
             types = types.to(x3.device)
             ids = ids.to(x3.device)
             x3_1 = x3[types == 0]
             x3_1_ids = ids[types == 0]
             x3_2 = x3[types == 1]
+        with torch.no_grad():
+            return self._forward_hot(x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt)
+
+    def _forward_hot(self, x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt):
+        attention_scores = None
+        if x3_1_seq is None:
             if x3_1_ids.numel() > 0:
                 x3_1_seq, x3_1_mask, _ = self._group_tracks(x3_1, x3_1_ids)
             else:

@@ -1,5 +1,6 @@
 """Retrieval front-ends over the engine: single-GPU search, the gallery-sharded multi-GPU
-search (one process per GPU, NCCL all-gather of the per-shard candidate lists), and the
+search (one process per GPU; the exchange is done by the kernels themselves over NVLink peer
+memory, an NCCL all-gather path is kept for stacks without symmetric memory), and the
 evaluation-script outputs (rank of the true shop item, top-k hit counts).
 
 The reference scores one query at a time on the CPU (evaluate_movingfashion.py:157-277,
@@ -142,11 +143,12 @@ class ShardedRetriever:
     with gloo.
     """
 
-    def __init__(self, ops, gallery_shard: torch.Tensor, shard_offset: int, group=None):
+    def __init__(self, ops, gallery_shard: torch.Tensor, shard_offset: int, group=None, world: Optional[int] = None,
+                 rank: Optional[int] = None):
         self.ops = ops
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         self.gallery = ops.prepare_gallery(gallery_shard, index_offset=shard_offset)
 
     @classmethod
@@ -179,80 +181,121 @@ class ShardedRetriever:
     def search(self, seq: torch.Tensor, mask: Optional[torch.Tensor], k: int = 20):
         return self.search_descriptors(self.aggregate(seq, mask), k)
 
-    def search_peer(self, seq: torch.Tensor, mask: Optional[torch.Tensor], k: int, peer: "PeerExchange"):
-        """Same result as ``search`` with both exchange steps done by P2P writes (``PeerExchange``) --
-        no NCCL call, capturable into a CUDA graph.  Needs Q divisible by the world size."""
-        Q = seq.shape[1]
-        lo, hi = shard_bounds(Q, self.world, self.rank)
-        peer.begin_step()
-        self.ops.aggregate(seq[:, lo:hi], None if mask is None else mask[lo:hi], out=peer.rows_out(lo, hi))
-        q = peer.share_rows(lo, hi)
-        self.ops.score_topk(q, self.gallery, k, out=peer.lists_out())
-        return self.ops.merge_topk(*peer.share_lists())
+    def search_peer(self, seq: torch.Tensor, mask: Optional[torch.Tensor], peer: "PeerExchange", lens=None):
+        """Same result as ``search`` with the exchange done by the kernels themselves (``PeerExchange``): three
+        library calls, no collective, no copy, no barrier -- capturable into one CUDA graph.  ``seq`` / ``mask`` hold
+        ALL Q tracks (each rank aggregates the slice it owns); returns the complete ``(Q,k)`` result on every rank
+        (views of the exchange's final buffers) or, for a non-replicating exchange, the owner's rows."""
+        lo, hi = peer.q_lo[self.rank], peer.q_lo[self.rank + 1]
+        self.ops.sharded_aggregate(peer, seq[:, lo:hi], None if mask is None else mask[lo:hi],
+                                   None if lens is None else lens[lo:hi])
+        self.ops.sharded_score_topk(peer, self.gallery)
+        return self.ops.sharded_merge(peer)
 
 
 # ----------------------------------------------------------------------------------------
-# the two exchange steps over NVLink peer memory instead of NCCL
+# the exchange steps done by the kernels over NVLink peer memory (csrc/exchange.cuh)
 # ----------------------------------------------------------------------------------------
+def exchange_layout(Q: int, k: int, world: int):
+    """Pure host logic of the sharded search: who owns which queries and how big the exchange buffers are.
+    Rank r owns queries ``[q_lo[r], q_lo[r+1])`` (contiguous, balanced): it aggregates their tracks and merges their
+    per-shard lists.  Returns a dict of ``q_lo`` (world+1 ints), ``own_max`` and the per-rank buffer shapes."""
+    if world < 1 or world > 8:
+        raise ValueError("the sharded search supports 1..8 ranks (one NVSwitch box)")
+    bounds = [shard_bounds(Q, world, r) for r in range(world)]
+    q_lo = [b[0] for b in bounds] + [Q]
+    own_max = max(max(hi - lo for lo, hi in bounds), 1)
+    return {"q_lo": q_lo, "own_max": own_max,
+            "q_all": (2, max(Q, 1), 256), "lists": (2, world, own_max, k), "final": (max(Q, 1), k), "flags": (3 * 8,)}
+
+
 class PeerExchange:
-    """The sharded search has two exchange steps: every rank needs all Q aggregated descriptors, and
-    every rank's (Q,k) lists have to meet for the merge.  Both payloads are a few MB, so what they cost
-    as NCCL collectives is launch latency on a 0.3 ms step -- and NCCL calls cannot be captured into the
-    step's CUDA graph on this stack.  Here each rank WRITES its part straight into every peer's buffer
-    (symmetric memory: the peers' buffers are mapped into this process, the copies are plain P2P stores
-    over NVLink / NVSwitch) and a device-side barrier on the symmetric signal pads orders them.  Every
-    operation is an ordinary stream operation, so the whole N-GPU step replays as ONE graph.
+    """Buffers + descriptor (``struct seam_exchange``) of the gallery-sharded search.
 
-    Buffers: ``q_all (Q,256)`` fp32 and ``lists (2,N,Q,k)`` (margins, indices bit-cast to fp32; the scores
-    are a function of the margins and are recomputed by the merge);
-    the kernels write their results straight into this rank's slices of the local buffers
-    (``rows_out`` / ``lists_out``), from where they are copied to the peers.
-    Raises at construction if symmetric memory is unavailable; callers then keep the NCCL path."""
+    The two things that cross GPUs per step -- every rank's aggregated descriptors (everybody needs all Q) and the
+    per-shard top-k lists (they meet at the rank that owns the query) -- plus the merged rows when every rank wants
+    the complete result are STORED BY THE PRODUCING KERNELS straight into the consumers' memory: the buffers are
+    symmetric memory (``torch.distributed._symmetric_memory``: every peer's buffer is mapped into this process),
+    the stores travel over NVLink / NVSwitch, and flag words written after the last store (release) and polled by
+    the consuming kernel before its first load (acquire) order them.  Descriptor and list buffers are
+    double-buffered by the parity of a device-side step counter, so there is no barrier anywhere in a step and the
+    whole step replays as ONE CUDA graph without a host-side argument changing.
 
-    def __init__(self, engine: SeamEngine, Q: int, k: int, group=None):
-        import torch.distributed._symmetric_memory as symm
+    ``world == 1`` (or ``local_peers``) uses plain device tensors -- the same kernels and protocol on one GPU."""
+
+    def __init__(self, engine: SeamEngine, Q: int, k: int, group=None, replicate: bool = True, local_peers=None):
+        from ._lib import SeamExchange
         self.engine = engine
-        self.group = group if group is not None else dist.group.WORLD
-        self.world = dist.get_world_size(self.group)
-        self.rank = dist.get_rank(self.group)
-        self.Q, self.k = int(Q), int(k)
         dev = engine.device
-        self._q = symm.empty((self.Q, 256), dtype=torch.float32, device=dev)
-        self._l = symm.empty((2, self.world, self.Q, self.k), dtype=torch.float32, device=dev)
-        self._scores = torch.empty((self.Q, self.k), dtype=torch.float32, device=dev)   # local only
-        self._hq = symm.rendezvous(self._q, self.group)
-        self._hl = symm.rendezvous(self._l, self.group)
-        others = [(self.rank + r) % self.world for r in range(1, self.world)]
-        self._q_peers = [self._hq.get_buffer(r, (self.Q, 256), torch.float32) for r in others]
-        self._l_peers = [self._hl.get_buffer(r, (2, self.world, self.Q, self.k), torch.float32) for r in others]
+        self.Q, self.k, self.replicate = int(Q), int(k), bool(replicate)
+        if local_peers is not None:                        # several "ranks" inside one process (protocol tests)
+            self.world, self.rank = local_peers["world"], local_peers["rank"]
+        elif group is None and not dist.is_initialized():
+            self.world, self.rank = 1, 0
+        else:
+            self.group = group if group is not None else dist.group.WORLD
+            self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lay = exchange_layout(self.Q, self.k, self.world)
+        self.q_lo, self.own_max = lay["q_lo"], lay["own_max"]
+        names = ["q_all", "list_margin", "list_idx", "flags"] + (["final_score", "final_margin", "final_idx"] if replicate else [])
+        shapes = {"q_all": lay["q_all"], "list_margin": lay["lists"], "list_idx": lay["lists"], "flags": lay["flags"],
+                  "final_score": lay["final"], "final_margin": lay["final"], "final_idx": lay["final"]}
+        dtypes = {"q_all": torch.float32, "list_margin": torch.float32, "list_idx": torch.int32, "flags": torch.int32,
+                  "final_score": torch.float32, "final_margin": torch.float32, "final_idx": torch.int32}
+        self._bufs, self._peers = {}, {}
+        if local_peers is not None:
+            shared = local_peers["shared"]                 # {rank: {name: tensor}} filled by every local rank
+            mine = {n: torch.zeros(shapes[n], dtype=dtypes[n], device=dev) for n in names}
+            shared[self.rank] = mine
+            self._bufs = mine
+            self._shared = shared
+        elif self.world == 1:
+            self._bufs = {n: torch.zeros(shapes[n], dtype=dtypes[n], device=dev) for n in names}
+            self._peers = {n: [self._bufs[n]] for n in names}
+        else:
+            import torch.distributed._symmetric_memory as symm
+            for n in names:
+                t = symm.empty(shapes[n], dtype=dtypes[n], device=dev)
+                t.zero_()
+                h = symm.rendezvous(t, self.group)
+                self._bufs[n] = t
+                self._peers[n] = [t if r == self.rank else h.get_buffer(r, shapes[n], dtypes[n]) for r in range(self.world)]
+            torch.cuda.synchronize(dev)
+            dist.barrier(self.group)                       # nobody signals into flags a peer has not zeroed yet
+        self._step = torch.ones(1, dtype=torch.int32, device=dev)
+        self._done = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.struct = SeamExchange()
+        if local_peers is None:
+            self._fill_struct()
 
-    def begin_step(self) -> None:
-        """Nobody may overwrite a buffer a peer is still reading from the previous step."""
-        self._hq.barrier(channel=2)
+    def _fill_struct(self):
+        """(Re)build the C descriptor from the peer tensors (local-peer mode: once every rank has allocated)."""
+        if hasattr(self, "_shared"):
+            names = list(self._bufs)
+            self._peers = {n: [self._shared[r][n] for r in range(self.world)] for n in names}
+        x = self.struct
+        x.world, x.rank, x.Q, x.k, x.own_max = self.world, self.rank, self.Q, self.k, self.own_max
+        for i, v in enumerate(self.q_lo):
+            x.q_lo[i] = v
+        for n, tensors in self._peers.items():
+            arr = getattr(x, n)
+            for r, t in enumerate(tensors):
+                arr[r] = t.data_ptr()
+        x.step = self._step.data_ptr()
+        x.done = self._done.data_ptr()
 
-    def rows_out(self, lo: int, hi: int) -> torch.Tensor:
-        """Where this rank's descriptors (rows [lo,hi) of q_all) are to be written."""
-        return self._q[lo:hi]
+    @property
+    def final(self):
+        """(scores, margins, idx): this rank's copy of the complete (Q,k) result of the last finished step."""
+        return self._bufs["final_score"], self._bufs["final_margin"], self._bufs["final_idx"]
 
-    def share_rows(self, lo: int, hi: int) -> torch.Tensor:
-        """Rows [lo,hi) of the local q_all -> every peer's q_all; returns the (complete) local q_all."""
-        for buf in self._q_peers:
-            buf[lo:hi].copy_(self._q[lo:hi], non_blocking=True)
-        self._hq.barrier(channel=0)
-        return self._q
+    def descriptors(self) -> torch.Tensor:
+        """Both parity halves of this rank's (Q,256) descriptor buffer (diagnostics / tests)."""
+        return self._bufs["q_all"]
 
-    def lists_out(self):
-        """Where this rank's (Q,k) scores, margins, idx are to be written."""
-        mine = self._l[:, self.rank]
-        return self._scores, mine[0], mine[1].view(torch.int32)
-
-    def share_lists(self):
-        """This rank's slot of the local list buffer -> the same slot on every peer; returns the gathered
-        (None, margins, idx) with (N,Q,k) contiguous views, ready for ``merge_topk``."""
-        for buf in self._l_peers:
-            buf[:, self.rank].copy_(self._l[:, self.rank], non_blocking=True)
-        self._hl.barrier(channel=1)
-        return None, self._l[0], self._l[1].view(torch.int32)
+    @property
+    def steps_done(self) -> int:
+        return int(self._step.item()) - 1
 
 
 # ----------------------------------------------------------------------------------------
@@ -332,20 +375,20 @@ def evaluate_products(engine: SeamEngine, frame_desc: torch.Tensor, frame_produc
     shop_desc = shop_desc.to(dev, torch.float32).contiguous()
     ks = list(k_thresholds)
 
-    engine.load_scorer(*frame_last)
-    shop = engine.prepare_gallery(shop_desc)             # operands depend on the scorer just loaded
-    fr, _ = engine.rank_of_target(frame_desc, shop, target[fp])
     big = torch.iinfo(torch.int32).max
-    best = torch.full((P,), big, dtype=torch.int32, device=dev).scatter_reduce(0, fp, fr, "amin")
-    cnt = torch.zeros((P,), dtype=torch.float32, device=dev).index_add_(0, fp, torch.ones_like(fr, dtype=torch.float32))
-    avg = torch.zeros((P, frame_desc.shape[1]), dtype=torch.float32, device=dev).index_add_(0, fp, frame_desc)
-    has = cnt > 0
-    avg = avg / cnt.clamp(min=1.0)[:, None]
-    ar, _ = engine.rank_of_target(avg, shop, target)
-    ar = torch.where(has, ar, torch.full_like(ar, big))
+    with engine.scorer(*frame_last):                     # the caller's scorer is put back on exit
+        shop = engine.prepare_gallery(shop_desc)         # operands depend on the scorer just loaded
+        fr, _ = engine.rank_of_target(frame_desc, shop, target[fp])
+        best = torch.full((P,), big, dtype=torch.int32, device=dev).scatter_reduce(0, fp, fr, "amin")
+        cnt = torch.zeros((P,), dtype=torch.float32, device=dev).index_add_(0, fp, torch.ones_like(fr, dtype=torch.float32))
+        avg = torch.zeros((P, frame_desc.shape[1]), dtype=torch.float32, device=dev).index_add_(0, fp, frame_desc)
+        has = cnt > 0
+        avg = avg / cnt.clamp(min=1.0)[:, None]
+        ar, _ = engine.rank_of_target(avg, shop, target)
+        ar = torch.where(has, ar, torch.full_like(ar, big))
 
-    engine.load_scorer(*aggr_last)
-    rep = evaluate_aggregated(engine, seq, mask, shop_aggr, target, ks)
+    with engine.scorer(*aggr_last):
+        rep = evaluate_aggregated(engine, seq, mask, shop_aggr, target, ks)
 
     def row(r, n):
         return [float((r < k).sum()) / max(1, n) for k in ks]
@@ -378,6 +421,7 @@ def evaluate_distance_fusions(engine: SeamEngine, frame_desc: torch.Tensor, fram
     shop = shop_desc.to(dev, torch.float32).contiguous()
     target = target.to(dev, torch.int64)
     P, G = int(target.shape[0]), int(shop.shape[0])
+    prev_last = engine._last
     engine.load_scorer(*frame_last)
     order = torch.argsort(fp, stable=True)
     counts = torch.bincount(fp, minlength=P)
@@ -409,4 +453,6 @@ def evaluate_distance_fusions(engine: SeamEngine, frame_desc: torch.Tensor, fram
                 ranks[r, p0:p1] = torch.where(has, before.sum(1), ranks[r, p0:p1])
         p0 = max(p1, p0 + 1)
     hits = torch.stack([torch.stack([(ranks[r] < k).sum() for k in k_thresholds]) for r in range(2)])
+    if prev_last is not None:
+        engine.load_scorer(*prev_last)                 # the caller's scorer is put back
     return ranks, hits

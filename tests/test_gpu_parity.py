@@ -344,3 +344,139 @@ def test_fullsize_t64_aggregation(weights, engine):
     assert (out[sample].cpu() - ref).abs().max() <= TOL_EMB
     perm = torch.randperm(Q, device=DEV, generator=gen)
     assert torch.equal(engine.aggregate(seq[:, perm].contiguous()), out[perm])
+
+
+def _sample_check(engine, weights, seq, mask, lens, g, k, sample, q, sc, mg, ix):
+    """`sample` queries of a full-size search against the oracle (aggregation + fp32 scorer + ranking)."""
+    m_s = None if mask is None else mask[sample].cpu()
+    if m_s is None:
+        m_s = torch.zeros(len(sample), seq.shape[0], dtype=torch.bool)
+    ref_q, _ = so.aggregate_tracks(seq[:, sample].cpu(), m_s, weights)
+    assert (q[sample].cpu() - ref_q).abs().max() <= TOL_EMB
+    x5 = so.pair_logits(q[sample].cpu(), g.cpu(), weights, chunk=8)
+    return assert_topk_matches(ix[sample], mg[sample], sc[sample], so.logit_margin(x5), so.match_scores(x5), k)
+
+
+def test_fullsize_cfg3_shape(weights, engine):
+    """BASELINE.json configs[2]: 10,000 short multi-image queries (T_i in {2,3,4}, ragged mask, Tmax = 4)
+    against a 50,000-item gallery with planted matches (seed 2): a 64-query sample
+    against the oracle, shards + merge = whole at the 2/4/8-GPU shard sizes, sortedness."""
+    Q, T, G, k = 10000, 4, 50000, 20
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    lens = torch.randint(2, 5, (Q,), device=DEV, generator=gen)
+    seq = torch.zeros(1 + T, Q, 256, device=DEV)
+    seq[1:] = torch.randn(T, Q, 256, device=DEV, generator=gen)
+    mask = torch.arange(1 + T, device=DEV)[None, :] > lens[:, None]
+    seq[1:] *= (~mask[:, 1:]).t()[:, :, None]
+    q = engine.aggregate(seq, mask)
+    assert torch.equal(q, engine.aggregate(seq, None, lens=lens))
+    g = torch.randn(G, 256, device=DEV, generator=gen)
+    g[:Q] = q + 0.1 * torch.randn(Q, 256, device=DEV, generator=gen)
+    sc, mg, ix, stats = engine.score_topk(q, engine.prepare_gallery(g), k, return_stats=True)
+    assert (mg[:, :-1] >= mg[:, 1:]).all()
+    sample = torch.arange(0, Q, Q // 64)[:64]
+    _sample_check(engine, weights, seq, mask, lens, g, k, sample, q, sc, mg, ix)
+    for n in (2, 8):
+        S, M, I = [], [], []
+        for r in range(n):
+            lo, hi = r * G // n, (r + 1) * G // n
+            s, d, i = engine.score_topk(q, engine.prepare_gallery(g[lo:hi], index_offset=lo), k)
+            S.append(s), M.append(d), I.append(i)
+        s, d, i = engine.merge_topk(None, torch.stack(M), torch.stack(I))
+        assert torch.equal(i, ix) and torch.equal(d, mg) and torch.equal(s, sc)
+
+
+def test_fullsize_cfg5_shard_shape(weights, engine):
+    """BASELINE.json configs[4] at its per-GPU shape on 8 GPUs: 10,000 queries x 10 frames against a 125,000-row
+    gallery shard whose rows carry a global index offset (seed 4).  A 64-query sample
+    against the oracle; planted matches (first 10,000 rows) are found where the oracle finds them."""
+    Q, T, G, k, off = 10000, 10, 125000, 20, 3 * 125000
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    seq = torch.zeros(1 + T, Q, 256, device=DEV)
+    seq[1:] = torch.randn(T, Q, 256, device=DEV, generator=gen)
+    q = engine.aggregate(seq)
+    g = torch.randn(G, 256, device=DEV, generator=gen)
+    g[:Q] = q + 0.1 * torch.randn(Q, 256, device=DEV, generator=gen)
+    sc, mg, ix = engine.score_topk(q, engine.prepare_gallery(g, index_offset=off), k)
+    assert (mg[:, :-1] >= mg[:, 1:]).all() and int(ix.min()) >= off and int(ix.max()) < off + G
+    sample = torch.arange(0, Q, Q // 64)[:64]
+    _sample_check(engine, weights, seq, None, None, g, k, sample, q, sc, mg, ix - off)
+
+
+def test_eval_script_fp16_operands(weights, engine):
+    """the eval script scores the aggregated descriptor with an fp16-ROUNDED gallery and
+    fp16-rounded `last` weights promoted to fp32 arithmetic (evaluate_movingfashion.py:82-92, 123-124, 263-267).
+    Feeding the kernels the same rounded operands reproduces its scores and its ranking (argsort descending,
+    :268) up to ties inside the stated tolerance."""
+    import numpy as np
+    Q, T, G, k = 48, 10, 3000, 20
+    seq, mask, _ = so.synth_tracks(Q, T, seed=11)
+    q, _ = so.aggregate_tracks(seq, mask, weights)                       # fp32 query (:262)
+    gal = so.synth_gallery(G, 11, q)
+    gal16 = gal.numpy().astype(np.float16)                               # shop_aggr stored as fp16 (:82-92)
+    W16 = weights["last.weight"].numpy().astype(np.float16)              # :123
+    B16 = weights["last.bias"].numpy().astype(np.float16)                # :124
+    ref = np.concatenate([so.eval_aggr_scores_np(gal16, q[i].numpy(), W16, B16) for i in range(Q)], 0)   # (Q,G)
+    assert ref.dtype == np.float32
+    with engine.scorer(torch.from_numpy(W16.astype(np.float32)), torch.from_numpy(B16.astype(np.float32))):
+        g = engine.prepare_gallery(torch.from_numpy(gal16.astype(np.float32)).to(DEV))
+        sc, mg, ix = engine.score_topk(q.to(DEV), g, k)
+        x5 = engine.score_dense(q.to(DEV), g.g).cpu()
+    ref_t = torch.from_numpy(ref)
+    # dense scores: softmax of the same fp32 logits
+    assert (torch.softmax(x5, -1)[..., 1] - ref_t).abs().max() <= TOL_SCORE
+    # ranking: the script's argsort order vs the fused top-k, ties inside the tolerance allowed
+    order = torch.from_numpy(so.eval_rankings_np(ref)[:, :k].copy())
+    got = ix.cpu().long()
+    assert (torch.gather(ref_t, 1, got) - sc.cpu()).abs().max() <= TOL_SCORE
+    differs = order != got
+    d_full = so.logit_margin(x5)
+    if differs.any():
+        assert ((torch.gather(d_full, 1, order) - torch.gather(d_full, 1, got)).abs()[differs] <= 2 * TOL_LOGIT).all()
+    # the engine's scorer is the module's again afterwards
+    s2, _, i2 = engine.score_topk(q.to(DEV), engine.prepare_gallery(gal.to(DEV)), 5)
+    r_s, _, r_i = so.rank_topk(so.pair_logits(q, gal, weights), 5)
+    assert torch.equal(i2.cpu().long(), r_i) and (s2.cpu() - r_s).abs().max() <= TOL_SCORE
+
+
+def test_prepared_gallery_follows_the_scorer(weights, engine):
+    """A gallery prepared under one `last` and used after another was loaded is re-prepared (its cg = dw . g^2
+    and overflow statistics belong to the old weights): results equal a fresh preparation."""
+    seq, mask, _ = so.synth_tracks(40, 6, seed=31)
+    q, _ = so.aggregate_tracks(seq, mask, weights)
+    gal = so.synth_gallery(2000, 31, q)
+    prepared = engine.prepare_gallery(gal.to(DEV))
+    w2 = torch.randn(2, 256) * 0.1
+    b2 = torch.randn(2) * 0.1
+    with engine.scorer(w2, b2):
+        a = engine.score_topk(q.to(DEV), prepared, 10)                   # stale -> re-prepared under (w2, b2)
+        b = engine.score_topk(q.to(DEV), engine.prepare_gallery(gal.to(DEV)), 10)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+        ra = engine.rank_of_target(q.to(DEV), prepared, torch.arange(40))
+        rb = engine.rank_of_target(q.to(DEV), gal.to(DEV), torch.arange(40))
+        assert torch.equal(ra[0], rb[0])
+    c = engine.score_topk(q.to(DEV), prepared, 10)                       # and back under the original scorer
+    r_s, r_d, r_i = so.rank_topk(so.pair_logits(q, gal, weights), 10)
+    assert torch.equal(c[2].cpu().long(), r_i)
+
+
+def test_load_weights_rejects_wrong_shapes(weights, engine):
+    bad = {k: v.clone() for k, v in weights.items()}
+    bad["newnlb.theta.weight"] = torch.zeros(64, 256, 1)
+    with pytest.raises(ValueError):
+        engine.load_weights({k: v.to(DEV) for k, v in bad.items()})
+    engine.load_weights({k: v.to(DEV) for k, v in weights.items()})
+
+
+def test_score_topk_in_query_slabs(weights, engine, monkeypatch):
+    """Very large evaluations are scored in slabs of queries that share one bounded workspace; the result does not
+    depend on the slab size."""
+    import seam_match_rcnn_b200 as pkg
+    eng_mod = __import__("sys").modules[pkg.__name__ + ".engine"]
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    q = torch.randn(5000, 256, device=DEV, generator=gen)
+    gal = engine.prepare_gallery(torch.randn(4000, 256, device=DEV, generator=gen))
+    whole = engine.score_topk(q, gal, 20)
+    monkeypatch.setattr(eng_mod, "SCORE_WS_LIMIT", 16 << 20)
+    slabs = engine.score_topk(q, gal, 20)
+    assert all(torch.equal(a, b) for a, b in zip(whole, slabs))

@@ -214,3 +214,29 @@ def test_scorer_partition_is_a_balanced_cover(Q, G, rank_variant):
     if total >= 4 * num_sms:
         # the last CTA takes the remainder (possibly less); nobody is far above the mean
         assert max(costs) <= 1.15 * (sum(costs) / len(costs)) + 2.0
+
+
+def test_modules_copy_and_pickle_without_the_engine():
+    """copy.deepcopy / pickle of a module that has run once (and so caches a ctypes-backed engine) work: the
+    engine is transient state, the copy re-creates its own on first use."""
+    import copy
+    import pickle
+    import seam_match_rcnn_b200 as pkg
+    m = pkg.TemporalAggregationNLB()
+    m.__dict__["_seam_engine"] = object()          # stands in for a SeamEngine (ctypes pointers are not picklable)
+    m.__dict__["_seam_key"] = ("k",)
+    c = copy.deepcopy(m)
+    assert "_seam_engine" not in c.__dict__ and "_seam_key" not in c.__dict__
+    r = pickle.loads(pickle.dumps(m))
+    assert "_seam_engine" not in r.__dict__
+    assert sorted(r.state_dict()) == sorted(m.state_dict())
+    assert "_seam_engine" in m.__dict__            # the original keeps its engine
+
+
+def test_match_predictor_embedding_keeps_its_graph():
+    """The conv tower runs under autograd as in the reference (models/match_head.py:67-69): only the kernel
+    outputs are detached."""
+    import seam_match_rcnn_b200 as pkg
+    m = pkg.MatchPredictor()
+    x = torch.randn(2, 256, 14, 14)
+    assert m.embed(x).requires_grad
