@@ -66,6 +66,7 @@ enum seam_kernel {
   SEAM_KERNEL_RESCORE = 4,      /* K3b */
   SEAM_KERNEL_EXACT = 5,        /* K3c exhaustive path */
   SEAM_KERNEL_PREP_GALLERY = 6,
+  SEAM_KERNEL_MERGE = 7,        /* merge_topk_kernel / merge_sharded_kernel */
 };
 int seam_profile_enable(seam_handle* h, int enable);
 int seam_profile_read(seam_handle* h, int kernel, double* total_ms, int* launches);

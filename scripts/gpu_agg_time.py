@@ -11,7 +11,7 @@ CLEAN = os.environ.get("SEAM_FLUSH_CLEAN", "1") != "0"   # read 256 MiB after th
 HBM = 6542.1
 CASES = [(15000, 10), (100000, 10), (100000, 4), (10000, 4), (100000, 16), (50000, 32), (100000, 64), (64, 10)]
 if len(sys.argv) > 2:
-    CASES = [(int(sys.argv[1]), int(sys.argv[2]))]
+    CASES = [(int(q), int(sys.argv[-1])) for q in sys.argv[1:-1]]
 for Q, T in CASES:
     seq = torch.randn(1 + T, Q, 256, device=dev)
     for _ in range(3):

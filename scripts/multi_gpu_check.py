@@ -24,32 +24,39 @@ if rank == 0:
     derr = (mg - mg1).abs().max().item()
     print(f"world={world}: sharded vs single-GPU top-{k}: indices identical={same} |margin diff|max={derr:.2e}")
     ok = same and derr <= 3e-5
-# the same search with both exchange steps as P2P writes into symmetric memory (no NCCL), eager and as a graph
-Qp = (Q // world) * world
+# the same search with the exchange done by the kernels over peer memory (no NCCL call, no copy, no barrier),
+# eager and as ONE replayed CUDA graph; Q need not divide by the world size
 try:
-    peer = pkg.PeerExchange(eng, Qp, k)
+    peer = pkg.PeerExchange(eng, Q, k)
 except Exception as ex:
     peer = None
     if rank == 0:
         print(f"world={world}: symmetric memory unavailable ({type(ex).__name__}: {ex}); NCCL path only")
 if peer is not None:
-    seq_p = seq[:, :Qp].contiguous()
-    sc2, mg2, ix2 = r.search_peer(seq_p, None, k, peer)
+    sc2, mg2, ix2 = [t.clone() for t in r.search_peer(seq, None, peer)]
     torch.cuda.synchronize()
     side = torch.cuda.Stream(device=dev); side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-        for _ in range(2): r.search_peer(seq_p, None, k, peer)
+        for _ in range(2): r.search_peer(seq, None, peer)
     torch.cuda.current_stream(dev).wait_stream(side); torch.cuda.synchronize(); dist.barrier()
     gph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(gph, capture_error_mode="thread_local"):
-        sc3, mg3, ix3 = r.search_peer(seq_p, None, k, peer)
-    for _ in range(3): gph.replay()
-    torch.cuda.synchronize()
+        out3 = r.search_peer(seq, None, peer)
+    # replay with DIFFERENT queries each time (the graph reads seq in place): parity halves and the step counter
+    ok3 = True
+    for it in range(4):
+        seq[1:] = torch.randn(T, Q, 256, generator=torch.Generator().manual_seed(100 + it)).to(dev)
+        dist.barrier()
+        gph.replay()
+        torch.cuda.synchronize()
+        ref = pkg.search(eng, seq, None, gal, k) if rank == 0 else None
+        if rank == 0:
+            ok3 = ok3 and all(torch.equal(a, b) for a, b in zip(out3, ref))
     if rank == 0:
-        same2 = torch.equal(ix2, ix1[:Qp]) and torch.equal(mg2, mg1[:Qp]) and torch.equal(sc2, sc1[:Qp])
-        same3 = torch.equal(ix3, ix1[:Qp]) and torch.equal(mg3, mg1[:Qp]) and torch.equal(sc3, sc1[:Qp])
-        print(f"world={world}: peer-memory exchange vs single-GPU: eager identical={same2}, graph replay identical={same3}")
-        ok = ok and same2 and same3
+        same2 = torch.equal(ix2, ix1) and torch.equal(mg2, mg1) and torch.equal(sc2, sc1)
+        print(f"world={world}: in-kernel exchange vs single-GPU: eager identical={same2}, 4 graph replays with new queries "
+              f"identical={ok3}, steps done={peer.steps_done}, watchdog={eng.watchdog_records()}")
+        ok = ok and same2 and ok3
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
 dist.barrier(); dist.destroy_process_group()

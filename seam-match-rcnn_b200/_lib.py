@@ -17,7 +17,7 @@ _HEADER = os.path.join(os.path.dirname(_build.HERE), "include", "seam_b200.h")
 SEAM_OK = 0
 STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "STATE"}
 KERNELS = {"aggregate": 0, "nlb_gemm": 1, "prep_queries": 2, "score": 3, "rescore": 4, "exact": 5,
-           "prep_gallery": 6}
+           "prep_gallery": 6, "merge": 7}
 SEAM_MAX_T = 64
 SEAM_MAX_K = 32
 SEAM_MAX_WORLD = 8

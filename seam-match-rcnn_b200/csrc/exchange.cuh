@@ -5,8 +5,11 @@
 // result, the merged rows.  All three are written by the producing kernel straight into the consumers'
 // memory (peer-mapped symmetric buffers: plain stores over NVLink), and ordered by flag words instead of
 // barriers or collectives:
-//   producer grid:  stores ... ; every CTA: __threadfence_system + atomic count; the LAST CTA writes
-//                   flags[kind][my rank] = step on every rank (st.release.sys)
+//   producer grid:  stores ... ; every CTA: __threadfence (device scope) + atomic count; the LAST CTA, having
+//                   observed every other CTA's count, issues ONE system-scope fence and writes
+//                   flags[kind][my rank] = step on every rank (st.release.sys).  Causality is transitive across
+//                   the two scopes, so the peers' acquire of the flag covers every CTA's stores -- a
+//                   system-scope fence in each of a few hundred CTAs cost ~15 us per kernel
 //   consumer grid:  first thing, CTA-wide: spin (ld.acquire.sys) until flags[kind][r] >= step for all r
 // The step number lives in device memory and is advanced by the last kernel of a step, so a whole
 // step replays as one CUDA graph.  Descriptor and list buffers are double-buffered by step parity: a
@@ -56,13 +59,14 @@ __device__ __forceinline__ int owner_of(const Exchange& x, int qi) {
 // Call from EVERY CTA of a producing grid, after a __syncthreads that follows its last store: returns true in
 // thread 0 of the grid's last CTA once every rank has been told (callers that must do something "after the
 // whole grid" -- advancing the step -- hang it on that).
-__device__ __forceinline__ bool signal_all(const Exchange& x, int kind, uint32_t step) {
+__device__ __forceinline__ bool signal_all(const Exchange& x, int kind, uint32_t step, bool stored = true) {
   if (threadIdx.x != 0) return false;
-  __threadfence_system();                                  // this CTA's peer stores before its count
+  if (stored) __threadfence();                             // this CTA's stores (ordered by the CTA barrier) before its count;
+                                                           // a CTA that stored nothing only needs to be counted
   const unsigned n = atomicAdd(x.done + kind, 1u);
   if (n != gridDim.x - 1) return false;
   x.done[kind] = 0u;                                       // ready for the next grid that uses this kind
-  __threadfence_system();
+  __threadfence_system();                                  // everything observed so far before the flags, system-wide
   for (int r = 0; r < x.world; ++r) st_release_sys(x.flags[r] + kind * MAX_WORLD + x.rank, step);
   return true;
 }

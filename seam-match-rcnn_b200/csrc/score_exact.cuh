@@ -561,9 +561,9 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
     }
     __syncthreads();
   }
-  if (p.x_on) {          // every list row of this step (re-score kernel before, this one now) is on its way
+  if (p.x_on) {          // every list row of this step (re-score kernel before: complete at its end; this one now) is on its way
     __syncthreads();
-    xchg::signal_all(p.x, xchg::KIND_L, xstep);
+    xchg::signal_all(p.x, xchg::KIND_L, xstep, (int)blockIdx.x < nrows);
   }
 }
 

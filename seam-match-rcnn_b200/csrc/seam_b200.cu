@@ -862,6 +862,7 @@ int seam_sharded_merge(seam_handle* h, const seam_exchange* x, float* out_score,
   DeviceGuard guard(h->device);
   const int own = e.q_lo[e.rank + 1] - e.q_lo[e.rank];
   const int grid = own > 0 ? (own + 7) / 8 : 1;
+  ProfileScope prof(h, SEAM_KERNEL_MERGE, static_cast<cudaStream_t>(stream_));
   exact::merge_sharded_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(e, out_score, out_margin, out_idx);
   SEAM_LAUNCHED(h, "merge_sharded_kernel");
   return SEAM_OK;
@@ -1035,6 +1036,7 @@ int seam_merge_topk(seam_handle* h, const float* scores, const float* margins, c
   if (!margins || !idx || !out_score || !out_margin || !out_idx)    // scores may be null: recomputed from the margins
     return fail(h, SEAM_ERR_BAD_ARG, "seam_merge_topk: null pointer");
   DeviceGuard guard(h->device);
+  ProfileScope prof(h, SEAM_KERNEL_MERGE, static_cast<cudaStream_t>(stream_));
   exact::merge_topk_kernel<<<(Q + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       scores, margins, idx, N, Q, k, out_score, out_margin, out_idx);
   SEAM_LAUNCHED(h, "merge_topk_kernel");

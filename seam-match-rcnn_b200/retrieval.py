@@ -79,10 +79,11 @@ class HostTrackStream:
         n = (seq_h.shape[0] - 1) * seq_h.shape[1] * seq_h.shape[2] * seq_h.element_size()
         return n + (mask_h.numel() * mask_h.element_size() if mask_h is not None else 0)
 
-    def chunks(self, seq_h: torch.Tensor, mask_h: Optional[torch.Tensor]):
-        """Yields (lo, hi, descriptors (hi-lo,256) on the device) per slice, in order, on the current stream."""
+    def uploads(self, seq_h: torch.Tensor, mask_h: Optional[torch.Tensor]):
+        """Yields (lo, hi, tracks (1+Tmax, hi-lo, 256), mask or None) per slice, in order, usable on the current
+        stream: all copies are enqueued on the copy stream first, the current stream waits for each slice's event."""
         eng, dev = self.engine, self.engine.device
-        T1, Q = seq_h.shape[0], seq_h.shape[1]
+        Q = seq_h.shape[1]
         main = torch.cuda.current_stream(dev)
         self.copy_stream.wait_stream(main)
         staged = []
@@ -101,7 +102,12 @@ class HostTrackStream:
             s_d.record_stream(main)
             if m_d is not None:
                 m_d.record_stream(main)
-            yield lo, hi, eng.aggregate(s_d, m_d)
+            yield lo, hi, s_d, m_d
+
+    def chunks(self, seq_h: torch.Tensor, mask_h: Optional[torch.Tensor]):
+        """Yields (lo, hi, descriptors (hi-lo,256) on the device) per slice, in order, on the current stream."""
+        for lo, hi, s_d, m_d in self.uploads(seq_h, mask_h):
+            yield lo, hi, self.engine.aggregate(s_d, m_d)
 
 
 def search_host(engine: SeamEngine, seq_h: torch.Tensor, mask_h: Optional[torch.Tensor], gallery_h: torch.Tensor,
@@ -149,7 +155,8 @@ class ShardedRetriever:
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
-        self.gallery = ops.prepare_gallery(gallery_shard, index_offset=shard_offset)
+        self.gallery = (gallery_shard if isinstance(gallery_shard, PreparedGallery)
+                        else ops.prepare_gallery(gallery_shard, index_offset=shard_offset))
 
     @classmethod
     def from_full_gallery(cls, ops, gallery: torch.Tensor, group=None):
