@@ -7,7 +7,7 @@
 // barriers or collectives:
 //   producer grid:  stores ... ; every CTA: __threadfence (device scope) + atomic count; the LAST CTA, having
 //                   observed every other CTA's count, issues ONE system-scope fence and writes
-//                   flags[kind][my rank] = step on every rank (st.release.sys).  Causality is transitive across
+//                   flags[kind][my rank] = step on every rank (relaxed stores after it).  Causality is transitive across
 //                   the two scopes, so the peers' acquire of the flag covers every CTA's stores -- a
 //                   system-scope fence in each of a few hundred CTAs cost ~15 us per kernel
 //   consumer grid:  first thing, CTA-wide: spin (ld.acquire.sys) until flags[kind][r] >= step for all r
@@ -44,8 +44,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t current_step(const Exchange& x) { return *reinterpret_cast<volatile uint32_t*>(x.step); }
 __device__ __forceinline__ int owner_of(const Exchange& x, int qi) {
@@ -66,8 +66,10 @@ __device__ __forceinline__ bool signal_all(const Exchange& x, int kind, uint32_t
   const unsigned n = atomicAdd(x.done + kind, 1u);
   if (n != gridDim.x - 1) return false;
   x.done[kind] = 0u;                                       // ready for the next grid that uses this kind
-  __threadfence_system();                                  // everything observed so far before the flags, system-wide
-  for (int r = 0; r < x.world; ++r) st_release_sys(x.flags[r] + kind * MAX_WORLD + x.rank, step);
+  // ONE system-scope fence orders everything observed so far before the flag stores (a release store per rank
+  // would repeat it world times: ~2 us each over NVLink)
+  __threadfence_system();
+  for (int r = 0; r < x.world; ++r) st_relaxed_sys(x.flags[r] + kind * MAX_WORLD + x.rank, step);
   return true;
 }
 // Spin until every rank's data of `kind` for `step` has landed here (watchdog: a peer that never shows up
