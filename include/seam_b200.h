@@ -165,6 +165,20 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
  * models/match_head.py:160-162 and MatchPredictor.forward :70-74. */
 int seam_score_dense(seam_handle* h, const float* q, int Q, const float* g, int G, float* x5, void* stream);
 
+/* Class-1 probabilities softmax(x5)[...,1] as a dense (Q,G) fp32 matrix: compute_distances
+ * (evaluate_movingfashion.py:101-106) and, with g = q, compute_selfdist (:115-121, the street x street matrix the
+ * tracker thresholds).  Small problems only (the fused entries never materialise it). */
+int seam_score_prob(seam_handle* h, const float* q, int Q, const float* g, int G, float* prob, void* stream);
+
+/* "AVG & MAX DISTANCE" fusions of the eval script (evaluate_movingfashion.py:294-316) for all products at once: per
+ * product the class-1 probabilities of its frames against every shop item are averaged / maximised over the frames
+ * and the rank of the true item in the descending order (ties: lower index first) is returned -- without the
+ * (frames x gallery) matrix ever existing, in the fp32 direct form.
+ *   frames (N,256) fp32 SORTED BY PRODUCT; start (P+1) int32 CSR offsets into it; target (P) int32 shop row;
+ *   rank_avg / rank_max (P) int32; products without frames get G. */
+int seam_rank_fused_distances(seam_handle* h, const float* frames, const int32_t* start, int P, const float* g, int G,
+                              const int32_t* target, int32_t* rank_avg, int32_t* rank_max, void* stream);
+
 /* Rank of one designated gallery item per query (0 = best), the quantity the eval script
  * reads out of its full argsort: evaluate_movingfashion.py:268-269.
  *   target (Q) int32 gallery row;  out_rank (Q) int32;  out_margin (Q) fp32 optional   */

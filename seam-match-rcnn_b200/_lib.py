@@ -114,6 +114,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_score_topk.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.seam_score_dense.restype = i32
     lib.seam_score_dense.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    lib.seam_score_prob.restype = i32
+    lib.seam_score_prob.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    lib.seam_rank_fused_distances.restype = i32
+    lib.seam_rank_fused_distances.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
     lib.seam_rank_of_target.restype = i32
     lib.seam_rank_of_target.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
     lib.seam_rank_workspace_bytes.restype = sz

@@ -569,6 +569,7 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
 
 // ---------------------------------------------------------------- dense logits
 // x5 (Q,G,2).  32 queries x 32 gallery rows per CTA, operands staged in shared memory.
+template <bool PROB>     // false: x5 (Q,G,2) logits; true: (Q,G) class-1 probabilities softmax(x5)[...,1]
 __global__ void __launch_bounds__(256) dense_logits_kernel(const float* __restrict__ q, int Q,
                                                            const float* __restrict__ g, int G,
                                                            const float* __restrict__ fold, float* __restrict__ x5) {
@@ -606,9 +607,118 @@ __global__ void __launch_bounds__(256) dense_logits_kernel(const float* __restri
   for (int u = 0; u < 4; ++u) {
     const int i = i0 + ty * 4 + u, j = j0 + tx;
     if (i < Q && j < G) {
-      float2 o = make_float2(l0[u] + b0, l1[u] + b1);
-      *reinterpret_cast<float2*>(x5 + ((size_t)i * G + j) * 2) = o;
+      if constexpr (PROB) {
+        x5[(size_t)i * G + j] = softmax1(l0[u] + b0, l1[u] + b1);
+      } else {
+        float2 o = make_float2(l0[u] + b0, l1[u] + b1);
+        *reinterpret_cast<float2*>(x5 + ((size_t)i * G + j) * 2) = o;
+      }
     }
+  }
+}
+
+// ---------------------------------------------------------------- per-product distance fusions
+// evaluate_movingfashion.py:294-316 ("AVG & MAX DISTANCE"): per product, the class-1 probabilities of its tracked
+// frames against every shop item (compute_distances, :101-106) are averaged / maximised over the frames and the
+// true shop item's position in the descending order is read off.  Here, for all products at once and without
+// ever materialising the (frames x gallery) matrix: a CTA takes one product x 1024 shop items, keeps the
+// product's frames (16 at a time) in shared memory, each warp scores shop rows in the fp32 direct form against
+// 4 frames per butterfly, and the per-item running sum / maximum live in shared memory; the target item's fused
+// values are computed by the same code path, then every item is compared with them and counted.
+//   frames (N,256) sorted by product, start (P+1) CSR offsets, target (P) shop row, ranks (P) zero-initialised.
+// Products without frames get rank G (as the eval script never ranks them).
+struct FusedDistParams {
+  const float* frames;
+  const int32_t* start;
+  const float* g;
+  const int32_t* target;
+  const float* fold;
+  int P, G;
+  int32_t* rank_avg;
+  int32_t* rank_max;
+};
+constexpr int FD_ROWS = 1024, FD_FRAMES = 16;
+
+__global__ void __launch_bounds__(256) fused_dist_rank_kernel(const FusedDistParams p) {
+  __shared__ __align__(16) float fs[FD_FRAMES][256];
+  __shared__ float acc_sum[FD_ROWS + 1], acc_max[FD_ROWS + 1];     // last slot: the target item
+  __shared__ int cnt_s[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prod = blockIdx.x, j0 = blockIdx.y * FD_ROWS;
+  const int f0 = p.start[prod], nf = p.start[prod + 1] - f0;
+  if (nf <= 0) {
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+      p.rank_avg[prod] = p.G;
+      p.rank_max[prod] = p.G;
+    }
+    return;
+  }
+  const int rows = min(FD_ROWS, p.G - j0);
+  const int tj = p.target[prod];
+  for (int i = threadIdx.x; i <= FD_ROWS; i += 256) {
+    acc_sum[i] = 0.f;
+    acc_max[i] = -INFINITY;
+  }
+  if (threadIdx.x < 2) cnt_s[threadIdx.x] = 0;
+  const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
+  const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
+  const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
+  for (int c0 = 0; c0 < nf; c0 += FD_FRAMES) {
+    const int nc = min(FD_FRAMES, nf - c0);
+    __syncthreads();                                   // previous chunk consumed (and the accumulators initialised)
+    for (int e = threadIdx.x; e < nc * 64; e += 256)
+      reinterpret_cast<float4*>(&fs[0][0])[e] = reinterpret_cast<const float4*>(p.frames + (size_t)(f0 + c0) * 256)[e];
+    __syncthreads();
+    for (int r = warp; r <= rows; r += 8) {            // r == rows: the target item
+      const int j = r < rows ? j0 + r : tj;
+      const int slot = r < rows ? r : FD_ROWS;
+      const Slice gs = load_slice(p.g + (size_t)j * 256, lane);
+      float sum = 0.f, mx = -INFINITY;
+      for (int fb = 0; fb < nc; fb += 4) {
+        float part[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const Slice fr = load_slice(&fs[min(fb + u, nc - 1)][0], lane);
+          sqdiff_dot2(fr, gs, w0, w1, part[2 * u], part[2 * u + 1]);
+        }
+        const float tot = ptx::treduce<8>(part, lane);   // lane l: total of part[l % 8]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float l0 = __shfl_sync(ptx::FULL_MASK, tot, 2 * u) + b0;
+          const float l1 = __shfl_sync(ptx::FULL_MASK, tot, 2 * u + 1) + b1;
+          if (fb + u < nc) {
+            const float pr = softmax1(l0, l1);
+            sum += pr;
+            mx = fmaxf(mx, pr);
+          }
+        }
+      }
+      if (lane == 0) {                                 // this warp owns the slot in this pass
+        acc_sum[slot] += sum;
+        acc_max[slot] = fmaxf(acc_max[slot], mx);
+      }
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)nf;
+  const float tavg = acc_sum[FD_ROWS] * inv, tmax = acc_max[FD_ROWS];
+  int ca = 0, cm = 0;
+  for (int i = threadIdx.x; i < rows; i += 256) {
+    const int j = j0 + i;
+    const float a = acc_sum[i] * inv, m = acc_max[i];
+    ca += (a > tavg || (a == tavg && j < tj)) ? 1 : 0;
+    cm += (m > tmax || (m == tmax && j < tj)) ? 1 : 0;
+  }
+  ca = __reduce_add_sync(ptx::FULL_MASK, ca);
+  cm = __reduce_add_sync(ptx::FULL_MASK, cm);
+  if (lane == 0) {
+    atomicAdd(&cnt_s[0], ca);
+    atomicAdd(&cnt_s[1], cm);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(p.rank_avg + prod, cnt_s[0]);
+    atomicAdd(p.rank_max + prod, cnt_s[1]);
   }
 }
 

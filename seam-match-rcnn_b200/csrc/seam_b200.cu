@@ -878,8 +878,53 @@ int seam_score_dense(seam_handle* h, const float* q, int Q, const float* g, int 
   DeviceGuard guard(h->device);
   dim3 grid((G + 31) / 32, (Q + 31) / 32);
   if (grid.y > 65535) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_dense: Q too large for the dense path");
-  exact::dense_logits_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(q, Q, g, G, h->fold, x5);
+  exact::dense_logits_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(q, Q, g, G, h->fold, x5);
   SEAM_LAUNCHED(h, "dense_logits_kernel");
+  return SEAM_OK;
+}
+
+int seam_score_prob(seam_handle* h, const float* q, int Q, const float* g, int G, float* prob, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_score_prob: scorer weights not loaded");
+  if (Q < 0 || G < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_prob: negative size");
+  if (Q == 0 || G == 0) return SEAM_OK;
+  if (!q || !g || !prob) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_prob: null pointer");
+  DeviceGuard guard(h->device);
+  dim3 grid((G + 31) / 32, (Q + 31) / 32);
+  if (grid.y > 65535) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_prob: Q too large for the dense path");
+  exact::dense_logits_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(q, Q, g, G, h->fold, prob);
+  SEAM_LAUNCHED(h, "dense_logits_kernel<prob>");
+  return SEAM_OK;
+}
+
+int seam_rank_fused_distances(seam_handle* h, const float* frames, const int32_t* start, int P, const float* g, int G,
+                              const int32_t* target, int32_t* rank_avg, int32_t* rank_max, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_scorer) return fail(h, SEAM_ERR_STATE, "seam_rank_fused_distances: scorer weights not loaded");
+  if (P < 0 || G <= 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_fused_distances: bad size");
+  if (P == 0) return SEAM_OK;
+  if (!start || !g || !target || !rank_avg || !rank_max)
+    return fail(h, SEAM_ERR_BAD_ARG, "seam_rank_fused_distances: null pointer");
+  if ((frames && !aligned16(frames)) || !aligned16(g))
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_fused_distances: 16-byte alignment");
+  const int chunks = (G + exact::FD_ROWS - 1) / exact::FD_ROWS;
+  if (chunks > 65535) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_rank_fused_distances: G too large");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  SEAM_CUDA(h, cudaMemsetAsync(rank_avg, 0, (size_t)P * 4, stream));
+  SEAM_CUDA(h, cudaMemsetAsync(rank_max, 0, (size_t)P * 4, stream));
+  exact::FusedDistParams fp;
+  fp.frames = frames;
+  fp.start = start;
+  fp.g = g;
+  fp.target = target;
+  fp.fold = h->fold;
+  fp.P = P;
+  fp.G = G;
+  fp.rank_avg = rank_avg;
+  fp.rank_max = rank_max;
+  exact::fused_dist_rank_kernel<<<dim3((unsigned)P, (unsigned)chunks), 256, 0, stream>>>(fp);
+  SEAM_LAUNCHED(h, "fused_dist_rank_kernel");
   return SEAM_OK;
 }
 

@@ -374,6 +374,32 @@ class SeamEngine:
                                                x5.data_ptr(), self._stream()))
         return x5
 
+    def score_prob(self, q: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+        """softmax(x5)[...,1] as a dense (Q,G) matrix: ``compute_distances`` of the eval script
+        (evaluate_movingfashion.py:101-106); with ``g = q`` its ``compute_selfdist`` (:115-121)."""
+        q, g = self._f32(q, "queries"), self._f32(g, "gallery")
+        out = torch.empty((q.shape[0], g.shape[0]), dtype=torch.float32, device=self.device)
+        self._check(self._lib.seam_score_prob(self._h, q.data_ptr(), q.shape[0], g.data_ptr(), g.shape[0],
+                                              out.data_ptr(), self._stream()))
+        return out
+
+    def rank_fused_distances(self, frames: torch.Tensor, start: torch.Tensor, g: torch.Tensor, target: torch.Tensor):
+        """Ranks of the true shop items under the per-product average / maximum of the frames' class-1
+        probabilities (evaluate_movingfashion.py:294-316).  ``frames (N,256)`` sorted by product, ``start (P+1)``
+        CSR offsets, ``target (P)``.  Returns ``(rank_avg, rank_max)`` int32 ``(P,)``; no host synchronisation."""
+        frames, g = self._f32(frames, "frames"), self._f32(g, "gallery")
+        s32 = start.to(device=self.device, dtype=torch.int32).contiguous()
+        t32 = target.to(device=self.device, dtype=torch.int32).contiguous()
+        P = int(t32.shape[0])
+        if s32.shape != (P + 1,):
+            raise ValueError("start must hold P+1 offsets")
+        ra = torch.empty((P,), dtype=torch.int32, device=self.device)
+        rm = torch.empty((P,), dtype=torch.int32, device=self.device)
+        self._check(self._lib.seam_rank_fused_distances(self._h, frames.data_ptr() if frames.numel() else 0,
+                                                        s32.data_ptr(), P, g.data_ptr(), g.shape[0], t32.data_ptr(),
+                                                        ra.data_ptr(), rm.data_ptr(), self._stream()))
+        return ra, rm
+
     def rank_of_target(self, q: torch.Tensor, g, target: torch.Tensor, return_stats: bool = False):
         """Rank (0 = best) of gallery row target[i] for query i: evaluate_movingfashion.py:268-269.
 

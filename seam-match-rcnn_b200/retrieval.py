@@ -412,54 +412,38 @@ def evaluate_products(engine: SeamEngine, frame_desc: torch.Tensor, frame_produc
 def evaluate_distance_fusions(engine: SeamEngine, frame_desc: torch.Tensor, frame_product: torch.Tensor,
                               shop_desc: torch.Tensor, target: torch.Tensor,
                               frame_last: Tuple[torch.Tensor, torch.Tensor],
-                              k_thresholds: Sequence[int] = K_THRESHOLDS, max_pairs: int = 1 << 25):
+                              k_thresholds: Sequence[int] = K_THRESHOLDS, max_pairs: Optional[int] = None):
     """The "Avg Dist" / "Max Dist" rows of the eval printout (evaluate_movingfashion.py:294-316): per product
     the (frames x gallery) matrix of class-1 probabilities is averaged / maximised over the product's frames
     and the true shop item's position in the descending order is read off.
 
-    Not a fused kernel: the probabilities come from the dense fp32 logits kernel (``seam_score_dense``, the
-    reference's own formula) in chunks of products of at most ``max_pairs`` pairs, the per-product mean / max
-    and the rank counts are torch reductions on the device.  Returns
-    ``(ranks (2,P) int64 [avg, max], hits (2, len(k_thresholds)) int64)``; ties rank by lower index first, like
-    ``seam_rank_of_target``."""
+    One fused kernel for all products (``seam_rank_fused_distances``): the (frames x gallery) matrix is never
+    materialised, nothing synchronises with the host (the frames are grouped by product with a device sort, the
+    hit counts are device reductions).  Returns ``(ranks (2,P) int64 [avg, max], hits (2, len(k_thresholds))
+    int64)``; products without frames get rank G; ties rank by lower index first, like ``seam_rank_of_target``.
+    ``max_pairs`` is accepted for compatibility and ignored."""
     dev = engine.device
-    frame_desc = frame_desc.to(dev, torch.float32).contiguous()
+    frame_desc = frame_desc.to(dev, torch.float32)
     fp = frame_product.to(dev, torch.int64)
     shop = shop_desc.to(dev, torch.float32).contiguous()
-    target = target.to(dev, torch.int64)
-    P, G = int(target.shape[0]), int(shop.shape[0])
-    prev_last = engine._last
-    engine.load_scorer(*frame_last)
+    P = int(target.shape[0])
     order = torch.argsort(fp, stable=True)
-    counts = torch.bincount(fp, minlength=P)
-    starts = torch.cumsum(counts, 0) - counts
-    counts_h, starts_h = counts.tolist(), starts.tolist()
-    ranks = torch.full((2, P), G, dtype=torch.int64, device=dev)
-    col = torch.arange(G, device=dev)
-    p0 = 0
-    while p0 < P:
-        p1, n = p0, 0
-        while p1 < P and (n + counts_h[p1]) * G <= max(max_pairs, counts_h[p1] * G):
-            n += counts_h[p1]
-            p1 += 1
-        if n > 0:
-            rows = order[starts_h[p0]:starts_h[p0] + n]
-            x5 = engine.score_dense(frame_desc[rows], shop)                     # (n,G,2)
-            prob = torch.softmax(x5, dim=-1)[..., 1]                            # :103-106
-            local = fp[rows] - p0
-            npr = p1 - p0
-            ssum = torch.zeros((npr, G), dtype=torch.float32, device=dev).index_add_(0, local, prob)
-            avg = ssum / counts[p0:p1].clamp(min=1).to(torch.float32)[:, None]  # distances.mean(0)
-            mx = torch.full((npr, G), -1.0, dtype=torch.float32, device=dev).scatter_reduce(
-                0, local[:, None].expand(-1, G), prob, "amax")                  # distances.max(0)
-            t = target[p0:p1]
-            has = counts[p0:p1] > 0
-            for r, fused in enumerate((avg, mx)):
-                ft = fused.gather(1, t[:, None])
-                before = (fused > ft) | ((fused == ft) & (col[None, :] < t[:, None]))
-                ranks[r, p0:p1] = torch.where(has, before.sum(1), ranks[r, p0:p1])
-        p0 = max(p1, p0 + 1)
-    hits = torch.stack([torch.stack([(ranks[r] < k).sum() for k in k_thresholds]) for r in range(2)])
-    if prev_last is not None:
-        engine.load_scorer(*prev_last)                 # the caller's scorer is put back
+    counts = torch.bincount(fp, minlength=P)[:P]
+    start = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    start[1:] = torch.cumsum(counts, 0)
+    frames = frame_desc.index_select(0, order).contiguous()
+    with engine.scorer(*frame_last):                         # the caller's scorer is put back on exit
+        ra, rm = engine.rank_fused_distances(frames, start, shop, target)
+    ranks = torch.stack([ra, rm]).to(torch.int64)
+    ks = torch.tensor(list(k_thresholds), device=dev)
+    hits = (ranks[:, :, None] < ks[None, None, :]).sum(1)
     return ranks, hits
+
+
+def self_distances(engine: SeamEngine, street_desc: torch.Tensor, frame_last: Tuple[torch.Tensor, torch.Tensor]):
+    """``compute_selfdist`` of the eval script (evaluate_movingfashion.py:115-121): the street x street matrix of
+    class-1 probabilities its tracker thresholds (:165-214), for the boxes of one frame group at a time
+    (n <= a few hundred: a dense (n,n) fp32 matrix, fp32 values of the script's fp16 formula)."""
+    x = street_desc.to(engine.device, torch.float32).contiguous()
+    with engine.scorer(*frame_last):
+        return engine.score_prob(x, x)

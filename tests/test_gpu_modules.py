@@ -249,4 +249,58 @@ def test_evaluate_distance_fusions(model, weights):
             near = int(((fused - fused[t]).abs() <= 1e-6).sum())          # ties inside fp32 rounding may swap
             assert abs(int(ranks[r, p]) - want) <= near, (p, r, int(ranks[r, p]), want)
     assert hits.shape == (2, 4)
+    for r in range(2):
+        assert hits[r].tolist() == [int((ranks[r] < k).sum()) for k in (1, 5, 10, 20)]
+
+
+def test_distance_fusions_against_the_eval_loop(model, weights):
+    """Larger case with many frames per product (several shared-memory frame chunks) and several gallery chunks,
+    against the oracle's literal per-product loop (eval_product_loop: avg_dist / max_dist)."""
+    P, G = 40, 2600
+    rs = np.random.RandomState(16)
+    lens = rs.randint(1, 40, size=P)
+    lens[7] = 0
+    frame_product = torch.tensor([p for p in range(P) for _ in range(int(lens[p]))])
+    perm = torch.from_numpy(rs.permutation(len(frame_product)))
+    frame_product = frame_product[perm]
+    frame_desc = torch.from_numpy(rs.randn(len(frame_product), 256).astype(np.float32))
+    shop_desc = torch.from_numpy(rs.randn(G, 256).astype(np.float32))
+    target = torch.from_numpy(rs.permutation(G)[:P].astype(np.int64))
+    fw = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2, 256)).astype(np.float32))
+    fb = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2,)).astype(np.float32))
+    eng = model._engine_for(torch.device(DEV))
+    before = eng._last
+    ranks, hits = pkg.evaluate_distance_fusions(eng, frame_desc, frame_product, shop_desc, target, (fw, fb))
+    assert eng._last[0].data_ptr() == before[0].data_ptr()       # the caller's scorer is back
+    wf = dict(weights)
+    wf["last.weight"], wf["last.bias"] = fw, fb
+    ref = so.eval_product_loop(frame_desc, frame_product, shop_desc, target, wf,
+                               torch.zeros(P, 256), shop_desc, wf)
+    prob = so.match_scores(so.pair_logits(frame_desc, shop_desc, wf))
+    for r, key in enumerate(("avg_dist", "max_dist")):
+        for p in range(P):
+            rows = (frame_product == p).nonzero().flatten()
+            if len(rows) == 0:
+                assert int(ranks[r, p]) == G
+                continue
+            fused = prob[rows].mean(0) if r == 0 else prob[rows].max(0).values
+            near = int(((fused - fused[int(target[p])]).abs() <= 1e-6).sum())
+            assert abs(int(ranks[r, p]) - int(ref[key][p])) <= near, (key, p)
+
+
+def test_self_distances(model, weights):
+    """compute_selfdist (evaluate_movingfashion.py:115-121): street x street class-1 probabilities."""
+    rs = np.random.RandomState(26)
+    x = torch.from_numpy(rs.randn(77, 256).astype(np.float32))
+    fw = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2, 256)).astype(np.float32))
+    fb = torch.from_numpy(rs.uniform(-1 / 16, 1 / 16, (2,)).astype(np.float32))
+    eng = model._engine_for(torch.device(DEV))
+    got = pkg.self_distances(eng, x, (fw, fb)).cpu()
+    wf = dict(weights)
+    wf["last.weight"], wf["last.bias"] = fw, fb
+    ref = so.match_scores(so.pair_logits(x, x, wf))
+    assert got.shape == (77, 77) and (got - ref).abs().max() <= 1e-5
+    # numpy-fp16 values of the script's own formula stay within fp16 resolution of the fp32 values
+    f16 = so.eval_frame_scores_np(x.numpy().astype(np.float16), x.numpy().astype(np.float16), fw.numpy(), fb.numpy())
+    assert np.abs(f16.astype(np.float32) - got.numpy()).max() <= 2e-2
     model._sync_weights(eng)
