@@ -67,6 +67,7 @@ enum seam_kernel {
   SEAM_KERNEL_EXACT = 5,        /* K3c exhaustive path */
   SEAM_KERNEL_PREP_GALLERY = 6,
   SEAM_KERNEL_MERGE = 7,        /* merge_topk_kernel / merge_sharded_kernel */
+  SEAM_KERNEL_TOWER = 8,        /* the whole conv tower (layout pass + 4 conv3x3_kernel + pool/linear/BN) */
 };
 int seam_profile_enable(seam_handle* h, int enable);
 int seam_profile_read(seam_handle* h, int kernel, double* total_ms, int* launches);
@@ -252,6 +253,27 @@ int seam_sharded_score_topk(seam_handle* h, const seam_exchange* x, const float*
  * the owner's rows. */
 int seam_sharded_merge(seam_handle* h, const seam_exchange* x, float* out_score, float* out_margin, int32_t* out_idx,
                        void* stream);
+
+/* ---- the match head's conv tower: ROI features -> 256-d embedding ---------------
+ * Replaces MatchPredictor's conv_seq / pool / linear in eval mode, models/match_head.py:50-62 as called at :67-69
+ * and :93-95:   4 x [Conv2d 3x3 valid + ReLU] (256 -> 256 -> 256 -> 256 -> 1024 channels, 14 -> 6 spatial),
+ * AvgPool2d(6) + ReLU, Linear(1024,256), BatchNorm1d(256) with its running statistics.
+ * The convolutions run as shifted GEMMs on the tensor cores (tcgen05, fp16 operands, fp32 accumulation: the
+ * precision class of the TF32 path cuDNN runs for the reference by default); results agree with the fp32 module
+ * to ~2e-3 of the output scale (tests state 1e-2).
+ *   conv_w[l] (Cout,256,3,3) fp32, conv_b[l] (Cout): conv_seq.{0,2,4,6}.{weight,bias}; lin_w (256,1024), lin_b (256):
+ *   linear.0; bn_*: linear.1.{weight,bias,running_mean,running_var}, bn_eps its eps.  The handle keeps its own
+ *   reorganised copy.
+ *   x (K,256,14,14) fp32 NCHW (the RoIAlign output the reference feeds, models/video_matchrcnn.py roi_features);
+ *   out: fp32 rows of 256; ROI i goes to row dst_row[i] (int64; NULL: row i) -- e.g. slot (1+t)*Q + track of the
+ *   time-major x3_1_seq (models/match_head.py:101-111), so the aggregation kernel reads what this one wrote.
+ *   workspace: seam_tower_workspace_bytes(K) bytes (about 330 KB per ROI), 1 KB aligned. */
+int seam_tower_load_weights(seam_handle* h, const float* const* conv_w, const float* const* conv_b, const float* lin_w,
+                            const float* lin_b, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                            const float* bn_var, float bn_eps, void* stream);
+size_t seam_tower_workspace_bytes(int K);
+int seam_tower_forward(seam_handle* h, const float* x, int K, float* out, const int64_t* dst_row, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* Host -> device upload of a slice of tracks, tracks [lo, hi) of a HOST x3_1_seq (1+Tmax, Q, 256) fp32
  * (the reference keeps every feature in host memory between the detector and the scorer,

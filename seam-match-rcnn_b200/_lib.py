@@ -17,7 +17,7 @@ _HEADER = os.path.join(os.path.dirname(_build.HERE), "include", "seam_b200.h")
 SEAM_OK = 0
 STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "STATE"}
 KERNELS = {"aggregate": 0, "nlb_gemm": 1, "prep_queries": 2, "score": 3, "rescore": 4, "exact": 5,
-           "prep_gallery": 6, "merge": 7}
+           "prep_gallery": 6, "merge": 7, "tower": 8}
 SEAM_MAX_T = 64
 SEAM_MAX_K = 32
 SEAM_MAX_WORLD = 8
@@ -131,6 +131,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_sharded_score_topk.argtypes = [vp, xp, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]
     lib.seam_sharded_merge.restype = i32
     lib.seam_sharded_merge.argtypes = [vp, xp, vp, vp, vp, vp]
+    lib.seam_tower_load_weights.restype = i32
+    lib.seam_tower_load_weights.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, vp, C.c_float, vp]
+    lib.seam_tower_workspace_bytes.restype = sz
+    lib.seam_tower_workspace_bytes.argtypes = [i32]
+    lib.seam_tower_forward.restype = i32
+    lib.seam_tower_forward.argtypes = [vp, vp, i32, vp, vp, vp, sz, vp]
     lib.seam_upload_tracks.restype = i32
     lib.seam_upload_tracks.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.seam_merge_topk.restype = i32

@@ -19,6 +19,7 @@
 #include "nlb_gemm.cuh"
 #include "score_exact.cuh"
 #include "score_tc.cuh"
+#include "tower_tc.cuh"
 
 using namespace seam;
 
@@ -36,6 +37,10 @@ struct seam_handle {
   uint64_t launches = 0;
   bool profiling = false;
   unsigned int* watchdog = nullptr;   // host-mapped record buffer of the device-side wait watchdogs
+  // conv tower (f3): reorganised fp16 conv weights, biases, transposed linear weight, folded BatchNorm
+  __half* tw_conv[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* tw_misc = nullptr;           // bias0..3 (256,256,256,1024) | lin_wt (1024*256) | lin_b | bn_scale | bn_shift
+  bool have_tower = false;
   // developer overrides, read once at seam_create (never consulted on the hot path)
   int dbg_score_grid = 0, dbg_agg_grid = 0, dbg_cta_ns = 0, score_nseed = 4;
   struct Span { int kernel; cudaEvent_t a, b; };
@@ -249,6 +254,7 @@ int seam_create(seam_handle** out, int device) {
                        (int)aggf::group_smem_bytes<2>());
   cudaFuncSetAttribute(aggf::aggregate_fused_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)aggf::group_smem_bytes<4>());
+  cudaFuncSetAttribute(tower::conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tower::SMEM_BYTES);
   cudaFuncSetAttribute(nlbgemm::nlb_full_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)((SEAM_MAX_T * 257 + 2 * SEAM_MAX_T) * sizeof(float)));
   if ((e = cudaGetLastError()) != cudaSuccess) {
@@ -267,6 +273,8 @@ void seam_destroy(seam_handle* h) {
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->free_events) cudaEventDestroy(e);
     cudaFree(h->fold);
+    for (int i = 0; i < 4; ++i) cudaFree(h->tw_conv[i]);
+    cudaFree(h->tw_misc);
   }
   delete h;
 }
@@ -1055,6 +1063,124 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
                                                                   out_margin);
   SEAM_LAUNCHED(h, "rank_of_target_kernel");
   if (stats) SEAM_CUDA(h, cudaMemcpyAsync(stats, counters, 4, cudaMemcpyDeviceToDevice, stream));
+  return SEAM_OK;
+}
+
+// ------------------------------------------------------------------------------ conv tower (f3)
+namespace {
+constexpr int TW_GUARD = 192;                                    // rows a shifted A box may reach past a layer's last position
+constexpr size_t TW_OFF_B[4] = {0, 256, 512, 768};               // biases inside tw_misc (floats)
+constexpr size_t TW_OFF_WT = 1792, TW_OFF_LB = TW_OFF_WT + 1024 * 256, TW_OFF_SC = TW_OFF_LB + 256,
+                 TW_OFF_SH = TW_OFF_SC + 256, TW_MISC_TOTAL = TW_OFF_SH + 256;
+const int TW_HW[5] = {14, 12, 10, 8, 6};
+struct TowerPlan {
+  size_t off[5], total;
+};
+TowerPlan plan_tower(int K) {
+  TowerPlan t;
+  size_t o = 0;
+  for (int l = 0; l < 5; ++l) {
+    t.off[l] = o;
+    const size_t rows = (size_t)K * TW_HW[l] * TW_HW[l] + (l < 4 ? TW_GUARD : 0);
+    o += align_up(rows * (l < 4 ? 256 : 1024) * 2, 1024);
+  }
+  t.total = o;
+  return t;
+}
+int encode_map_fp16_2d(seam_handle* h, CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+  const cuuint64_t dims[2] = {inner, rows};
+  const cuuint64_t strides[1] = {inner * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)tower::BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, SEAM_ERR_CUDA, "cuTensorMapEncodeTiled (tower) failed with CUresult %d", (int)r);
+  return SEAM_OK;
+}
+}  // namespace
+
+int seam_tower_load_weights(seam_handle* h, const float* const* conv_w, const float* const* conv_b, const float* lin_w,
+                            const float* lin_b, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                            const float* bn_var, float bn_eps, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!conv_w || !conv_b || !lin_w || !lin_b || !bn_gamma || !bn_beta || !bn_mean || !bn_var)
+    return fail(h, SEAM_ERR_BAD_ARG, "seam_tower_load_weights: null pointer");
+  for (int l = 0; l < 4; ++l)
+    if (!conv_w[l] || !conv_b[l]) return fail(h, SEAM_ERR_BAD_ARG, "seam_tower_load_weights: null conv parameter %d", l);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  for (int l = 0; l < 4; ++l) {
+    const int cout = l < 3 ? 256 : 1024;
+    if (!h->tw_conv[l]) SEAM_CUDA(h, cudaMalloc(&h->tw_conv[l], (size_t)cout * 2304 * 2));
+  }
+  if (!h->tw_misc) SEAM_CUDA(h, cudaMalloc(&h->tw_misc, TW_MISC_TOTAL * 4));
+  for (int l = 0; l < 4; ++l) {
+    const int cout = l < 3 ? 256 : 1024;
+    tower::conv_weight_rows_kernel<<<cout, 256, 0, stream>>>(conv_w[l], h->tw_conv[l], cout);
+    SEAM_LAUNCHED(h, "conv_weight_rows_kernel");
+    SEAM_CUDA(h, cudaMemcpyAsync(h->tw_misc + TW_OFF_B[l], conv_b[l], (size_t)cout * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  SEAM_CUDA(h, cudaMemcpyAsync(h->tw_misc + TW_OFF_LB, lin_b, 256 * 4, cudaMemcpyDeviceToDevice, stream));
+  tower::tower_fold_kernel<<<256, 256, 0, stream>>>(lin_w, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, h->tw_misc + TW_OFF_WT,
+                                                    h->tw_misc + TW_OFF_SC, h->tw_misc + TW_OFF_SH);
+  SEAM_LAUNCHED(h, "tower_fold_kernel");
+  h->have_tower = true;
+  return SEAM_OK;
+}
+
+size_t seam_tower_workspace_bytes(int K) { return K > 0 ? plan_tower(K).total : 1024; }
+
+int seam_tower_forward(seam_handle* h, const float* x, int K, float* out, const int64_t* dst_row, void* workspace,
+                       size_t workspace_bytes, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!h->have_tower) return fail(h, SEAM_ERR_STATE, "seam_tower_forward: tower weights not loaded");
+  if (K < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_tower_forward: negative size");
+  if (K == 0) return SEAM_OK;
+  if ((long long)K * 196 > 0x7fffff00ll) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_tower_forward: K too large");
+  if (!x || !out || !workspace) return fail(h, SEAM_ERR_BAD_ARG, "seam_tower_forward: null pointer");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023u)) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_tower_forward: workspace must be 1 KB aligned");
+  const TowerPlan tp = plan_tower(K);
+  if (workspace_bytes < tp.total) return fail(h, SEAM_ERR_STATE, "seam_tower_forward: workspace too small (%zu < %zu)", workspace_bytes, tp.total);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  ProfileScope prof(h, SEAM_KERNEL_TOWER, stream);
+  tower::nchw_to_rows_kernel<<<dim3((unsigned)K, 8), 256, 0, stream>>>(x, reinterpret_cast<__half*>(ws + tp.off[0]), K);
+  SEAM_LAUNCHED(h, "nchw_to_rows_kernel");
+  for (int l = 0; l < 4; ++l) {
+    const int H = TW_HW[l], cout = l < 3 ? 256 : 1024;
+    const long long rows_in = (long long)K * H * H;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if ((rc = encode_map_fp16_2d(h, &tmA, ws + tp.off[l], 256, (uint64_t)rows_in + TW_GUARD, tower::BM)) != SEAM_OK) return rc;
+    if ((rc = encode_map_fp16_2d(h, &tmB, h->tw_conv[l], 2304, (uint64_t)cout, tower::BN)) != SEAM_OK) return rc;
+    tower::ConvParams cp;
+    cp.H = H;
+    cp.W = H;
+    cp.K = K;
+    cp.Cout = cout;
+    cp.rows_in = rows_in;
+    cp.m_tiles = (int)((rows_in + tower::BM - 1) / tower::BM);
+    cp.n_tiles = cout / tower::BN;
+    cp.bias = h->tw_misc + TW_OFF_B[l];
+    cp.out = reinterpret_cast<__half*>(ws + tp.off[l + 1]);
+    const long long total = (long long)cp.m_tiles * cp.n_tiles;
+    const int grid = total < h->num_sms ? (int)total : h->num_sms;
+    tower::conv3x3_kernel<<<grid, tower::THREADS, tower::SMEM_BYTES, stream>>>(tmA, tmB, cp);
+    SEAM_LAUNCHED(h, "conv3x3_kernel");
+  }
+  tower::PoolLinearParams pp;
+  pp.a4 = reinterpret_cast<const __half*>(ws + tp.off[4]);
+  pp.wt = h->tw_misc + TW_OFF_WT;
+  pp.lin_b = h->tw_misc + TW_OFF_LB;
+  pp.bn_scale = h->tw_misc + TW_OFF_SC;
+  pp.bn_shift = h->tw_misc + TW_OFF_SH;
+  pp.dst_row = reinterpret_cast<const long long*>(dst_row);
+  pp.out = out;
+  pp.K = K;
+  tower::pool_linear_bn_kernel<<<(K + tower::PL_ROIS - 1) / tower::PL_ROIS, 256, 0, stream>>>(pp);
+  SEAM_LAUNCHED(h, "pool_linear_bn_kernel");
   return SEAM_OK;
 }
 

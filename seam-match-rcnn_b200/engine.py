@@ -178,6 +178,60 @@ class SeamEngine:
             if prev is not None:
                 self.load_scorer(*prev)
 
+    # ------------------------------------------------------------------ conv tower
+    TOWER_KEYS = ("conv_seq.0", "conv_seq.2", "conv_seq.4", "conv_seq.6")
+
+    def load_tower(self, state: Mapping[str, torch.Tensor], prefix: str = "", bn_eps: float = 1e-5) -> None:
+        """Upload the match head's conv tower (``conv_seq.{0,2,4,6}``, ``linear.0``, ``linear.1`` incl. running
+        statistics: models/match_head.py:50-62) in the layout the tensor-core kernels read."""
+        shapes = {"conv_seq.0.weight": (256, 256, 3, 3), "conv_seq.2.weight": (256, 256, 3, 3),
+                  "conv_seq.4.weight": (256, 256, 3, 3), "conv_seq.6.weight": (1024, 256, 3, 3),
+                  "conv_seq.0.bias": (256,), "conv_seq.2.bias": (256,), "conv_seq.4.bias": (256,), "conv_seq.6.bias": (1024,),
+                  "linear.0.weight": (256, 1024), "linear.0.bias": (256,), "linear.1.weight": (256,), "linear.1.bias": (256,),
+                  "linear.1.running_mean": (256,), "linear.1.running_var": (256,)}
+        t = {}
+        for key, shape in shapes.items():
+            k = prefix + key
+            if k not in state:
+                raise KeyError(f"state_dict is missing '{k}'")
+            if tuple(state[k].shape) != shape:
+                raise ValueError(f"'{k}' has shape {tuple(state[k].shape)}, expected {shape}")
+            t[key] = self._f32(state[k].detach(), k)
+        cw = (C.c_void_p * 4)(*[t[f"{n}.weight"].data_ptr() for n in self.TOWER_KEYS])
+        cb = (C.c_void_p * 4)(*[t[f"{n}.bias"].data_ptr() for n in self.TOWER_KEYS])
+        self._check(self._lib.seam_tower_load_weights(
+            self._h, cw, cb, t["linear.0.weight"].data_ptr(), t["linear.0.bias"].data_ptr(), t["linear.1.weight"].data_ptr(),
+            t["linear.1.bias"].data_ptr(), t["linear.1.running_mean"].data_ptr(), t["linear.1.running_var"].data_ptr(),
+            float(bn_eps), self._stream()))
+        self._tower_refs = t          # keep alive until the preparation kernels have run
+
+    def tower_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      dst_row: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``(K,256,14,14)`` ROI features -> 256-d embeddings (eval-mode ``conv_seq`` + ``pool`` + ``linear``,
+        models/match_head.py:67-69).  ``out``: fp32 rows of 256 to write into (default: a new ``(K,256)``);
+        ``dst_row (K,) int64``: the row of ``out`` each ROI goes to (default: its own index)."""
+        if x.dim() != 4 or tuple(x.shape[1:]) != (D_MODEL, 14, 14):
+            raise ValueError(f"ROI features must be (K,256,14,14), got {tuple(x.shape)}")
+        x = self._f32(x, "roi features")
+        K = x.shape[0]
+        if out is None:
+            if dst_row is not None:
+                raise ValueError("dst_row needs an explicit out")
+            out = torch.empty((K, D_MODEL), dtype=torch.float32, device=self.device)
+        if out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous() or out.shape[-1] != D_MODEL:
+            raise ValueError("out must be a contiguous fp32 tensor of rows of 256 on the engine's device")
+        d64 = None
+        if dst_row is not None:
+            d64 = dst_row.to(device=self.device, dtype=torch.int64).contiguous()
+            if d64.shape != (K,):
+                raise ValueError("dst_row must hold one row index per ROI")
+        nbytes = int(self._lib.seam_tower_workspace_bytes(K))
+        ws = self._workspace("tower", nbytes + 1024)
+        base = (ws.data_ptr() + 1023) & ~1023
+        self._check(self._lib.seam_tower_forward(self._h, x.data_ptr() if K else 0, K, out.data_ptr(), _ptr(d64), base,
+                                                 nbytes, self._stream()))
+        return out
+
     # ------------------------------------------------------------------ (a) aggregation
     def _out(self, out: Optional[torch.Tensor], shape, dtype, name: str) -> torch.Tensor:
         """A caller-provided output (e.g. a slice of a peer-shared buffer) or a fresh tensor."""

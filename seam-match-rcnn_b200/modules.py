@@ -26,7 +26,7 @@ class _EngineMixin:
     """Lazily creates a SeamEngine on the module's device and keeps its folded weights in
     sync with the module's parameters."""
 
-    _TRANSIENT = ("_seam_engine", "_seam_key", "_seam_epoch", "_gallery_cache")
+    _TRANSIENT = ("_seam_engine", "_seam_key", "_seam_epoch", "_gallery_cache", "_seam_tower_key", "_seam_tower_engine")
 
     def __getstate__(self):
         # the engine wraps a ctypes handle (not picklable, not copyable): copy.deepcopy(model), pickle and
@@ -119,11 +119,40 @@ class MatchPredictor(_EngineMixin, nn.Module):
         self.linear = nn.Sequential(nn.Linear(1024, 256), nn.BatchNorm1d(256))
         self.last = nn.Linear(256, 2)
 
-    # ---- feature producer (PyTorch) ------------------------------------------------
-    def embed(self, x):
-        """conv tower -> 256-d embedding (models/match_head.py:67-69 / :93-95)."""
+    # ---- conv tower -> 256-d embedding (models/match_head.py:67-69 / :93-95) ---------------
+    def embed_torch(self, x):
+        """The PyTorch modules themselves (training, CPU, and the reference the kernels are tested against)."""
         x2 = self.pool(self.conv_seq(x))
         return self.linear(x2.view(x2.size(0), -1))
+
+    def _tower_ready(self, x) -> bool:
+        """Eval mode on a CUDA tensor: the tensor-core tower (inference kernels: BatchNorm with running statistics,
+        no autograd history).  Training mode keeps the PyTorch modules (batch statistics, autograd)."""
+        return (not self.training) and x.is_cuda and x.dim() == 4 and tuple(x.shape[1:]) == (256, 14, 14)
+
+    def _sync_tower(self, eng: SeamEngine) -> None:
+        names = [k for k in self.state_dict(keep_vars=True) if k.startswith(("conv_seq.", "linear."))]
+        sd = self.state_dict(keep_vars=True)
+        key = tuple((k, sd[k].data_ptr(), sd[k]._version) for k in names) + (self.linear[1].eps,)
+        if self.__dict__.get("_seam_tower_key") != key or self.__dict__.get("_seam_tower_engine") is not eng:
+            eng.load_tower(sd, bn_eps=self.linear[1].eps)
+            self.__dict__["_seam_tower_key"] = key
+            self.__dict__["_seam_tower_engine"] = eng
+
+    def embed(self, x, out=None, dst_row=None):
+        """conv tower -> 256-d embedding.  Eval mode on CUDA: ``seam_tower_forward`` (tcgen05 shifted-GEMM
+        convolutions, fp16 operands / fp32 accumulation, fused pool + linear + BatchNorm); otherwise PyTorch."""
+        if self._tower_ready(x):
+            eng = self._engine_for(x.device)
+            self._sync_tower(eng)
+            with torch.no_grad():
+                return eng.tower_forward(x, out=out, dst_row=dst_row)
+        y = self.embed_torch(x)
+        if out is not None:
+            rows = dst_row if dst_row is not None else torch.arange(y.shape[0], device=y.device)
+            out.view(-1, y.shape[1])[rows] = y
+            return out
+        return y
 
     # ---- engine plumbing --------------------------------------------------------------
     def _hot_state(self):
@@ -187,7 +216,9 @@ class TemporalAggregationNLB(MatchPredictor):
 
     # ---- x-branch grouping: match_head.py:96-111 without the per-track host syncs --------
     @staticmethod
-    def _group_tracks(x3_1, ids):
+    def _group_layout(ids):
+        """Track index and frame position of every street ROI (tracks in ascending id order, frames in arrival
+        order: models/match_head.py:104-110): (inv, pos, counts, n_seqs, maxlen)."""
         uniq, inv = torch.unique(ids, sorted=True, return_inverse=True)
         n_seqs = uniq.numel()
         counts = torch.bincount(inv, minlength=n_seqs)
@@ -197,6 +228,11 @@ class TemporalAggregationNLB(MatchPredictor):
         pos_sorted = torch.arange(inv.numel(), device=inv.device) - starts[inv[order]]
         pos = torch.empty_like(pos_sorted)
         pos[order] = pos_sorted
+        return inv, pos, counts, n_seqs, maxlen
+
+    @classmethod
+    def _group_tracks(cls, x3_1, ids):
+        inv, pos, counts, n_seqs, maxlen = cls._group_layout(ids)
         seq = torch.zeros((1 + maxlen, n_seqs, D_MODEL), device=x3_1.device, dtype=x3_1.dtype)
         seq[1 + pos, inv] = x3_1
         mask = torch.arange(1 + maxlen, device=x3_1.device).unsqueeze(0) > counts.unsqueeze(1)
@@ -215,6 +251,27 @@ class TemporalAggregationNLB(MatchPredictor):
         ``score_topk`` beyond).  The conv tower of the x-branch runs under autograd (``x3_2`` keeps its graph);
         aggregation and scorer outputs are detached (inference kernels)."""
         x3_1 = x3_1_ids = None
+        if x3_1_seq is None and self._tower_ready(x):          # x-branch, eval: the tower writes the track layout itself
+            with torch.no_grad():
+                types = types.to(x.device)
+                ids = ids.to(x.device)
+                street = (types == 0).nonzero().flatten()
+                shop = (types == 1).nonzero().flatten()
+                x3_1_ids = ids[street]
+                if street.numel() > 0:
+                    inv, pos, counts, n_seqs, maxlen = self._group_layout(x3_1_ids)
+                    base = (1 + maxlen) * n_seqs
+                    buf = torch.zeros((base + shop.numel(), D_MODEL), device=x.device, dtype=torch.float32)
+                    dst = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
+                    dst[street] = (1 + pos) * n_seqs + inv      # slot (1 + t, track) of the time-major x3_1_seq
+                    dst[shop] = base + torch.arange(shop.numel(), device=x.device)
+                    self.embed(x, out=buf, dst_row=dst)
+                    x3_1_seq = buf[:base].view(1 + maxlen, n_seqs, D_MODEL)
+                    x3_1_mask = torch.arange(1 + maxlen, device=x.device).unsqueeze(0) > counts.unsqueeze(1)
+                    x3_2 = buf[base:]
+                    return self._forward_hot(None, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt, from_x=True)
+                x3_2 = self.embed(x)[shop]
+                return self._forward_hot(None, x3_1_ids, None, None, x3_2, getatt, from_x=True)
         if x3_1_seq is None:                                   # x-branch: match_head.py:92-111
             x3 = self.embed(x)                                 # under autograd, as in the reference
             types = types.to(x3.device)
@@ -225,9 +282,11 @@ class TemporalAggregationNLB(MatchPredictor):
         with torch.no_grad():
             return self._forward_hot(x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt)
 
-    def _forward_hot(self, x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt):
+    def _forward_hot(self, x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt, from_x=False):
         attention_scores = None
-        if x3_1_seq is None:
+        if from_x:
+            pass                                      # x-branch with the layout already written by the tower
+        elif x3_1_seq is None:
             if x3_1_ids.numel() > 0:
                 x3_1_seq, x3_1_mask, _ = self._group_tracks(x3_1, x3_1_ids)
             else:
