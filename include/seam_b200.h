@@ -254,6 +254,33 @@ int seam_sharded_score_topk(seam_handle* h, const seam_exchange* x, const float*
 int seam_sharded_merge(seam_handle* h, const seam_exchange* x, float* out_score, float* out_margin, int32_t* out_idx,
                        void* stream);
 
+/* ---- backward of the hot path, for training ---------------------------------------
+ * The reference trains through the aggregator with autograd: its losses consume x5 of TemporalAggregationNLB's
+ * x-branch (models/match_head.py:339, 429; stuffs/engine.py:158-185).  These entries give the vector-Jacobian
+ * products the forward entries need to sit inside an autograd graph (the Python host wraps them in
+ * torch.autograd.Function).  The forward kernels run on folded weights; the backward recomputes each track in the
+ * reference's un-folded formulation (models/nlb.py:66-101, match_head.py:144-151) and differentiates that.
+ *
+ * seam_aggregate_backward: dout (Q,256) = d loss / d x3_1b  ->  dseq (1+Tmax,Q,256) contiguous fp32 = d loss / d
+ * x3_1_seq (the caller zero-fills it: row 0 and padded frames stay zero) and the parameter gradients, ACCUMULATED
+ * into the buffers of `grads` (same shapes as the weights; the caller zero-fills them).  Tracks of at most 16
+ * frames (training uses about 10: train_movingfashion.py:165).  `w` holds the un-folded parameters (last_* unused). */
+typedef struct seam_weight_grads {
+  float* theta_w; float* theta_b;
+  float* phi_w;   float* phi_b;
+  float* g_w;     float* g_b;
+  float* W_w;     float* W_b;
+  float* concat_w;
+  float* att_w;   float* att_b;
+} seam_weight_grads;
+int seam_aggregate_backward(seam_handle* h, const seam_weights* w, const float* seq, const uint8_t* mask,
+                            const int32_t* lens, int Tmax, int Q, int64_t frame_stride, int64_t track_stride,
+                            const float* dout, float* dseq, const seam_weight_grads* grads, void* stream);
+/* Backward of seam_score_dense (x5 = last((q - g)^2), models/match_head.py:160-162): dx5 (Q,G,2) -> dq (Q,256),
+ * dg (G,256) (overwritten) and dlast_w (2,256), dlast_b (2) (accumulated; the caller zero-fills them). */
+int seam_score_dense_backward(seam_handle* h, const float* last_w, const float* q, int Q, const float* g, int G,
+                              const float* dx5, float* dq, float* dg, float* dlast_w, float* dlast_b, void* stream);
+
 /* ---- the match head's conv tower: ROI features -> 256-d embedding ---------------
  * Replaces MatchPredictor's conv_seq / pool / linear in eval mode, models/match_head.py:50-62 as called at :67-69
  * and :93-95:   4 x [Conv2d 3x3 valid + ReLU] (256 -> 256 -> 256 -> 256 -> 1024 channels, 14 -> 6 spatial),

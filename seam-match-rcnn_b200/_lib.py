@@ -50,6 +50,12 @@ class SeamExchange(C.Structure):
                 ("step", C.c_void_p), ("done", C.c_void_p)]
 
 
+class SeamWeightGrads(C.Structure):
+    """struct seam_weight_grads: gradient buffers of the 11 aggregator parameters (state_dict order)."""
+    FIELDS = ("theta_w", "theta_b", "phi_w", "phi_b", "g_w", "g_b", "W_w", "W_b", "concat_w", "att_w", "att_b")
+    _fields_ = [(n, C.c_void_p) for n in FIELDS]
+
+
 # field of seam_weights -> key in TemporalAggregationNLB.state_dict()
 WEIGHT_KEYS = {
     "theta_w": "newnlb.theta.weight", "theta_b": "newnlb.theta.bias",
@@ -131,6 +137,11 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_sharded_score_topk.argtypes = [vp, xp, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]
     lib.seam_sharded_merge.restype = i32
     lib.seam_sharded_merge.argtypes = [vp, xp, vp, vp, vp, vp]
+    lib.seam_aggregate_backward.restype = i32
+    lib.seam_aggregate_backward.argtypes = [vp, C.POINTER(SeamWeights), vp, vp, vp, i32, i32, i64, i64, vp, vp,
+                                            C.POINTER(SeamWeightGrads), vp]
+    lib.seam_score_dense_backward.restype = i32
+    lib.seam_score_dense_backward.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.seam_tower_load_weights.restype = i32
     lib.seam_tower_load_weights.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, vp, C.c_float, vp]
     lib.seam_tower_workspace_bytes.restype = sz

@@ -15,6 +15,7 @@
 
 #include "../../include/seam_b200.h"
 #include "aggregate_fused.cuh"
+#include "backward.cuh"
 #include "fold.cuh"
 #include "nlb_gemm.cuh"
 #include "score_exact.cuh"
@@ -254,6 +255,8 @@ int seam_create(seam_handle** out, int device) {
                        (int)aggf::group_smem_bytes<2>());
   cudaFuncSetAttribute(aggf::aggregate_fused_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)aggf::group_smem_bytes<4>());
+  cudaFuncSetAttribute(bwd::agg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)bwd::agg_bwd_smem_bytes(bwd::BWD_MAX_T));
   cudaFuncSetAttribute(tower::conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tower::SMEM_BYTES);
   cudaFuncSetAttribute(nlbgemm::nlb_full_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)((SEAM_MAX_T * 257 + 2 * SEAM_MAX_T) * sizeof(float)));
@@ -1063,6 +1066,58 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
                                                                   out_margin);
   SEAM_LAUNCHED(h, "rank_of_target_kernel");
   if (stats) SEAM_CUDA(h, cudaMemcpyAsync(stats, counters, 4, cudaMemcpyDeviceToDevice, stream));
+  return SEAM_OK;
+}
+
+// ------------------------------------------------------------------------------ backward (f4)
+int seam_aggregate_backward(seam_handle* h, const seam_weights* w, const float* seq, const uint8_t* mask,
+                            const int32_t* lens, int Tmax, int Q, int64_t frame_stride, int64_t track_stride,
+                            const float* dout, float* dseq, const seam_weight_grads* grads, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!w || !grads) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate_backward: weights / grads struct is null");
+  if (Q < 0 || Tmax < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate_backward: negative size");
+  if (Q == 0 || Tmax == 0) return SEAM_OK;
+  if (Tmax > bwd::BWD_MAX_T)
+    return fail(h, SEAM_ERR_UNSUPPORTED, "seam_aggregate_backward: Tmax=%d exceeds the %d frames per track the training path supports",
+                Tmax, bwd::BWD_MAX_T);
+  if (!seq || !dout || !dseq) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate_backward: null pointer");
+  const float* const* wp = reinterpret_cast<const float* const*>(w);
+  float* const* gp = reinterpret_cast<float* const*>(grads);
+  for (int i = 0; i < 11; ++i)
+    if (!wp[i] || !gp[i]) return fail(h, SEAM_ERR_BAD_ARG, "seam_aggregate_backward: null weight / gradient pointer %d", i);
+  DeviceGuard guard(h->device);
+  bwd::AggBwdParams p;
+  p.seq = seq;
+  p.mask = mask;
+  p.lens = lens;
+  p.Tmax = Tmax;
+  p.Q = Q;
+  p.frame_stride = frame_stride;
+  p.track_stride = track_stride;
+  p.dout = dout;
+  p.dseq = dseq;
+  p.w = {w->theta_w, w->theta_b, w->phi_w, w->phi_b, w->g_w, w->g_b, w->W_w, w->W_b, w->concat_w, w->att_w, w->att_b};
+  p.g = {grads->theta_w, grads->theta_b, grads->phi_w, grads->phi_b, grads->g_w, grads->g_b,
+         grads->W_w,     grads->W_b,     grads->concat_w, grads->att_w, grads->att_b};
+  bwd::agg_backward_kernel<<<Q, 256, bwd::agg_bwd_smem_bytes(Tmax), static_cast<cudaStream_t>(stream_)>>>(p);
+  SEAM_LAUNCHED(h, "agg_backward_kernel");
+  return SEAM_OK;
+}
+
+int seam_score_dense_backward(seam_handle* h, const float* last_w, const float* q, int Q, const float* g, int G,
+                              const float* dx5, float* dq, float* dg, float* dlast_w, float* dlast_b, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (Q < 0 || G < 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_score_dense_backward: negative size");
+  if (Q == 0 || G == 0) return SEAM_OK;
+  if (!last_w || !q || !g || !dx5 || !dq || !dg || !dlast_w || !dlast_b)
+    return fail(h, SEAM_ERR_BAD_ARG, "seam_score_dense_backward: null pointer");
+  if ((reinterpret_cast<uintptr_t>(dx5) & 7u)) return fail(h, SEAM_ERR_UNSUPPORTED, "seam_score_dense_backward: dx5 alignment");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  bwd::scorer_backward_q_kernel<<<Q, 256, 0, stream>>>(q, Q, g, G, last_w, dx5, dq, dlast_w, dlast_b);
+  SEAM_LAUNCHED(h, "scorer_backward_q_kernel");
+  bwd::scorer_backward_g_kernel<<<G, 256, 0, stream>>>(q, Q, g, G, last_w, dx5, dg);
+  SEAM_LAUNCHED(h, "scorer_backward_g_kernel");
   return SEAM_OK;
 }
 

@@ -13,7 +13,7 @@ from typing import Dict, Mapping, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import SeamError, SeamWeights, WEIGHT_KEYS
+from ._lib import SeamError, SeamWeightGrads, SeamWeights, WEIGHT_KEYS
 
 D_MODEL = 256
 # shapes of the reference's hot-path parameters (TemporalAggregationNLB().state_dict())
@@ -177,6 +177,34 @@ class SeamEngine:
         finally:
             if prev is not None:
                 self.load_scorer(*prev)
+
+    # ------------------------------------------------------------------ backward
+    def aggregate_backward(self, seq: torch.Tensor, mask, lens, params: Mapping[str, torch.Tensor], dout: torch.Tensor):
+        """Vector-Jacobian product of ``aggregate``: ``dout (Q,256)`` -> ``(dseq (1+Tmax,Q,256), {field: grad})`` for
+        the 11 aggregator parameters (fields of ``struct seam_weights``, un-folded fp32 tensors in ``params``)."""
+        seq, m8, l32, Tmax, Q = self._tracks(seq, mask, lens)
+        dout = self._f32(dout, "dout")
+        tensors = {f: self._f32(params[f].detach(), f) for f in SeamWeightGrads.FIELDS}
+        w = SeamWeights(**{f: (tensors[f].data_ptr() if f in tensors else 0) for f in SeamWeights.FIELDS})
+        grads = {f: torch.zeros_like(tensors[f]) for f in SeamWeightGrads.FIELDS}
+        gs = SeamWeightGrads(**{f: grads[f].data_ptr() for f in SeamWeightGrads.FIELDS})
+        dseq = torch.zeros((1 + Tmax, Q, D_MODEL), dtype=torch.float32, device=self.device)
+        self._check(self._lib.seam_aggregate_backward(self._h, C.byref(w), seq.data_ptr() if Q else 0, _ptr(m8), _ptr(l32),
+                                                      Tmax, Q, seq.stride(0), seq.stride(1), dout.data_ptr() if Q else 0,
+                                                      dseq.data_ptr(), C.byref(gs), self._stream()))
+        return dseq, grads
+
+    def score_dense_backward(self, q: torch.Tensor, g: torch.Tensor, last_w: torch.Tensor, dx5: torch.Tensor):
+        """Vector-Jacobian product of ``score_dense``: ``dx5 (Q,G,2)`` -> ``(dq, dg, dlast_w, dlast_b)``."""
+        q, g = self._f32(q, "queries"), self._f32(g, "gallery")
+        lw, dx5 = self._f32(last_w.detach(), "last_w"), self._f32(dx5, "dx5")
+        dq, dg = torch.zeros_like(q), torch.zeros_like(g)
+        dw = torch.zeros((2, D_MODEL), dtype=torch.float32, device=self.device)
+        db = torch.zeros((2,), dtype=torch.float32, device=self.device)
+        self._check(self._lib.seam_score_dense_backward(self._h, lw.data_ptr(), q.data_ptr(), q.shape[0], g.data_ptr(),
+                                                        g.shape[0], dx5.data_ptr(), dq.data_ptr(), dg.data_ptr(),
+                                                        dw.data_ptr(), db.data_ptr(), self._stream()))
+        return dq, dg, dw, db
 
     # ------------------------------------------------------------------ conv tower (SURVEY.md section 8 f3)
     TOWER_KEYS = ("conv_seq.0", "conv_seq.2", "conv_seq.4", "conv_seq.6")

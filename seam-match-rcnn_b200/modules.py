@@ -20,6 +20,40 @@ from ._lib import SeamError
 from .engine import D_MODEL, PreparedGallery, SeamEngine
 
 DENSE_PAIR_LIMIT = 1 << 26   # x5 is (Q,G,2) fp32: 512 MiB at this many pairs
+_AGG_FIELDS = ("theta_w", "theta_b", "phi_w", "phi_b", "g_w", "g_b", "W_w", "W_b", "concat_w", "att_w", "att_b")
+
+
+class _AggregateFn(torch.autograd.Function):
+    """x3_1b = aggregate(x3_1_seq) inside an autograd graph: forward = the fused aggregation kernel (folded
+    weights), backward = seam_aggregate_backward (the un-folded block re-derived per track)."""
+
+    @staticmethod
+    def forward(ctx, eng, seq, mask, *params):
+        ctx.eng, ctx.mask = eng, mask
+        ctx.save_for_backward(seq, *params)
+        return eng.aggregate(seq, mask)
+
+    @staticmethod
+    def backward(ctx, dout):
+        seq, *params = ctx.saved_tensors
+        dseq, grads = ctx.eng.aggregate_backward(seq, ctx.mask, None, dict(zip(_AGG_FIELDS, params)), dout.contiguous())
+        return (None, dseq, None) + tuple(grads[f].view_as(p) for f, p in zip(_AGG_FIELDS, params))
+
+
+class _PairLogitsFn(torch.autograd.Function):
+    """x5 = last((q - g)^2) (models/match_head.py:160-162) inside an autograd graph."""
+
+    @staticmethod
+    def forward(ctx, eng, q, g, last_w, last_b):
+        ctx.eng = eng
+        ctx.save_for_backward(q, g, last_w)
+        return eng.score_dense(q, g)
+
+    @staticmethod
+    def backward(ctx, dx5):
+        q, g, last_w = ctx.saved_tensors
+        dq, dg, dw, db = ctx.eng.score_dense_backward(q, g, last_w, dx5.contiguous())
+        return None, dq, dg, dw, db
 
 
 class _EngineMixin:
@@ -279,8 +313,36 @@ class TemporalAggregationNLB(MatchPredictor):
             x3_1 = x3[types == 0]
             x3_1_ids = ids[types == 0]
             x3_2 = x3[types == 1]
+        if torch.is_grad_enabled() and self.training and not getatt:
+            return self._forward_train(x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2)
         with torch.no_grad():
             return self._forward_hot(x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt)
+
+    def _agg_params(self):
+        n = self.newnlb
+        return (n.theta.weight, n.theta.bias, n.phi.weight, n.phi.bias, n.g.weight, n.g.bias, n.W.weight, n.W.bias,
+                n.concat_project[0].weight, self.attention_scorer.weight, self.attention_scorer.bias)
+
+    def _forward_train(self, x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2):
+        """Training (models/match_head.py:339, 429 call this forward under autograd): the same kernels forward,
+        ``seam_aggregate_backward`` / ``seam_score_dense_backward`` behind them, the grouping of ROI embeddings into
+        tracks as differentiable index operations.  x5 carries the graph the losses differentiate."""
+        if not self.nlb:
+            raise NotImplementedError("training with nlb=False is not supported by the CUDA path")
+        if x3_1_seq is None:
+            if x3_1_ids.numel() == 0:
+                return None, x3_2, None, None, None, x3_1_ids
+            x3_1_seq, x3_1_mask, _ = self._group_tracks(x3_1, x3_1_ids)      # index_put: differentiable w.r.t. x3_1
+        else:
+            x3_1_ids = torch.zeros((1, 2))
+        eng = self._engine_for(x3_1_seq.device)
+        self._sync_weights(eng)
+        x3_1b = _AggregateFn.apply(eng, x3_1_seq, x3_1_mask, *self._agg_params())
+        g = x3_2.to(x3_1b.device).reshape(-1, D_MODEL)
+        if x3_1b.shape[0] * g.shape[0] > DENSE_PAIR_LIMIT:
+            raise SeamError(2, "x5 too large for the training path")
+        x5 = _PairLogitsFn.apply(eng, x3_1b, g, self.last.weight, self.last.bias)
+        return x3_1b, x3_2, x5, x3_1_seq, x3_1_mask, x3_1_ids
 
     def _forward_hot(self, x3_1, x3_1_ids, x3_1_seq, x3_1_mask, x3_2, getatt, from_x=False):
         attention_scores = None
