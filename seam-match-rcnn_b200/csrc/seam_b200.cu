@@ -126,11 +126,27 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int TR>
-static void launch_aggregate_warp(const aggf::Params& p, int num_sms, cudaStream_t stream) {   // num_sms = CTA cap
+static void launch_aggregate_warp(seam_handle* h, aggf::Params& p, int num_sms, cudaStream_t stream) {   // num_sms = CTA cap
   constexpr int NW = aggf::Cfg<TR>::NW;
   const int want = (p.Q + NW - 1) / NW;
   const int grid = want < num_sms ? want : num_sms;
-  aggf::aggregate_fused_warp_kernel<TR><<<grid, aggf::warp_threads<TR>(), aggf::warp_smem_bytes<TR>(), stream>>>(p);
+  // full tracks (len == Tmax == TR) are fetched with one 3-D tensor-map copy: box {256, 1 track, TR frames} over
+  // seq viewed as (1+Tmax, Q, 256) with the caller's strides
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  p.use_tm = 0;
+  if (p.Tmax == TR && p.seq && (p.track_stride * 4) % 16 == 0 && (p.frame_stride * 4) % 16 == 0 &&
+      p.track_stride >= 256 && p.frame_stride >= 256) {
+    const cuuint64_t dims[3] = {256, (cuuint64_t)p.Q, (cuuint64_t)(1 + p.Tmax)};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.track_stride * 4, (cuuint64_t)p.frame_stride * 4};
+    const cuuint32_t box[3] = {256, 1, (cuuint32_t)TR};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (h->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.seq), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      p.use_tm = 1;
+  }
+  aggf::aggregate_fused_warp_kernel<TR><<<grid, aggf::warp_threads<TR>(), aggf::warp_smem_bytes<TR>(), stream>>>(tm, p);
 }
 template <int GW>
 static void launch_aggregate_group(const aggf::Params& p, int num_sms, cudaStream_t stream) {
@@ -408,9 +424,9 @@ static int aggregate_impl(seam_handle* h, const xchg::Exchange* x, int row0, int
     }
     return SEAM_OK;
   }
-  if (Tmax <= 4) launch_aggregate_warp<4>(p, cap, stream);
-  else if (Tmax <= 10) launch_aggregate_warp<10>(p, cap, stream);
-  else if (Tmax <= 16) launch_aggregate_warp<16>(p, cap, stream);
+  if (Tmax <= 4) launch_aggregate_warp<4>(h, p, cap, stream);
+  else if (Tmax <= 10) launch_aggregate_warp<10>(h, p, cap, stream);
+  else if (Tmax <= 16) launch_aggregate_warp<16>(h, p, cap, stream);
   else if (Tmax <= 32) launch_aggregate_group<2>(p, cap, stream);   // two warps per track
   else launch_aggregate_group<4>(p, cap, stream);                   // 33..64 frames: four warps per track
   SEAM_LAUNCHED(h, "aggregate kernel");

@@ -115,6 +115,19 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Wait of a warp that has nothing else to do and whose event is microseconds away (the aggregation kernel's helper
+// warps between batches): poll, then really sleep between polls -- a try_wait loop, even with a suspend-time hint,
+// kept waking often enough to execute ~10 % of the kernel's instructions and take issue slots from the producers.
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, uint32_t sleep_ns, uint32_t tag = 0) {
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 2000000000ull) watchdog_trap(tag, smem_u32(bar), parity);
+  }
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -129,6 +142,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// 3-D tiled tensor load with an L2 eviction-priority hint
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 // 1-D bulk copy global -> shared (no tensor map): size multiple of 16 B, 16 B aligned
