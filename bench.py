@@ -258,8 +258,7 @@ class Workload:
         if self.G == 0:                                               # aggregation only (cfg 4)
             return eng.aggregate(self.seq, self.mask)
         if self.world == 1:
-            q = eng.aggregate(self.seq, self.mask)
-            return eng.score_topk(q, self.gallery, self.k)
+            return eng.search(self.seq, self.mask, self.gallery, self.k)[1:]     # one library call (seam_search)
         if self.peer is not None:
             return self.retr.search_peer(self.seq, self.mask, self.peer)
         return self.retr.search(self.seq, self.mask, self.k)        # NCCL all-gather fallback (eager)
@@ -338,6 +337,8 @@ def run_ours(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # pinned host buffers (the e2e leg) should live on the NUMA node this GPU hangs off
+    numa = pkg.bind_to_gpu_numa_node(dev) if os.environ.get("SEAM_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -558,6 +559,7 @@ def run_ours(args):
                        "l2": "256 MiB buffer written between timed iterations",
                        "launch": parity.pop("_launch"),
                        "e2e_launch": "one CUDA graph replay per step (H2D, kernels, D2H)" if e2e_graph is not None else "eager",
+                       "host_numa_node": numa,
                        "parallelism": parity.pop("_parallelism")},
             "queries_per_sec": Q / (ms * 1e-3),
             "e2e": {"value": Q * G / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -162,6 +162,16 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
                     const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin,
                     int32_t* out_idx, int32_t* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* seam_aggregate + seam_score_topk in one call: tracks in, descriptors (q_out (Q,256) = x3_1b) and per-query top-k
+ * out -- the whole per-product loop body evaluate_movingfashion.py:252-277 for all products at once; same results as
+ * the two calls.  (Writing the scorer's per-query operands from the aggregation kernel's read-back instead of the
+ * prepare-queries pass was measured and dropped: the extra registers slowed the aggregation by more than the 6 us the
+ * pass costs inside a graph -- DESIGN.md.)  workspace: seam_score_workspace_bytes(h, Q, G, k). */
+int seam_search(seam_handle* h, const float* seq, const uint8_t* mask, const int32_t* lens, int Tmax, int Q,
+                int64_t frame_stride, int64_t track_stride, float* q_out, const float* g, const void* g16, const float* cg,
+                const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin, int32_t* out_idx,
+                int32_t* stats, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Dense logits (parity / small problems): x5 (Q,G,2) fp32 = last((q-g)^2).
  * models/match_head.py:160-162 and MatchPredictor.forward :70-74. */
 int seam_score_dense(seam_handle* h, const float* q, int Q, const float* g, int G, float* x5, void* stream);

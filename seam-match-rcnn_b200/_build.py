@@ -14,8 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libseam_b200.so")
 INFO_PATH = os.path.join(HERE, "libseam_b200.buildinfo")
 SOURCES = ["seam_b200.cu"]
-HEADERS = ["sm100_ptx.cuh", "warp_sort.cuh", "fold.cuh", "aggregate_fused.cuh", "nlb_gemm.cuh",
-           "score_tc.cuh", "score_exact.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh"))   # every header goes into the content hash
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 # SEAM_BUILD_DIAGNOSTICS=1 also compiles the scorer's measurement variants (partial epilogues, selected at

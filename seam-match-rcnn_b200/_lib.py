@@ -118,6 +118,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_score_plan.argtypes = [vp, i32, i32, C.POINTER(C.c_int64)]
     lib.seam_score_topk.restype = i32
     lib.seam_score_topk.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    lib.seam_search.restype = i32
+    lib.seam_search.argtypes = [vp, vp, vp, vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.seam_score_dense.restype = i32
     lib.seam_score_dense.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     lib.seam_score_prob.restype = i32

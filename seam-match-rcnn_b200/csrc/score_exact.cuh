@@ -23,6 +23,29 @@ constexpr float FP16_MAX = 65504.f;
 constexpr float EPS_COEFF = 9.9e-4f;   // 2^-10 = 9.77e-4, plus accumulation slack
 constexpr float TAG_REL_ERR = 8e-6f;   // > 2^-17 = 7.63e-6: 6 mantissa bits replaced by a column tag
 
+// The scorer's work decomposition as the re-score / resolve kernels need it: CTA b of the tensor-core pass swept the
+// linearised tiles [tb[b], tb[b+1]); a query tile's sweep was shared by `pieces` consecutive CTAs, each of which wrote
+// 4 sub-lists per row (count + group maxima, every call).  Slots beyond a row's pieces hold stale data from other
+// problem shapes and are never looked at -- so nothing has to be reset between calls.
+constexpr int PLAN_MAX_GRID = 160;
+struct PiecePlan {
+  int ntiles_n, nb;
+  int tb[PLAN_MAX_GRID + 1];
+};
+__device__ __forceinline__ int plan_cta_of_tile(const PiecePlan& pl, long long t) {
+  int lo = 0, hi = pl.nb - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)pl.tb[mid] <= t) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ int plan_pieces_of_row(const PiecePlan& pl, int qi) {
+  const long long r0 = (long long)(qi >> 7) * pl.ntiles_n;            // query tiles of 128 rows (score::BM)
+  return plan_cta_of_tile(pl, r0 + pl.ntiles_n - 1) - plan_cta_of_tile(pl, r0) + 1;
+}
+
 __device__ __forceinline__ float softmax1(float l0, float l1) {
   const float m = fmaxf(l0, l1);
   const float e0 = expf(l0 - m), e1 = expf(l1 - m);
@@ -121,8 +144,6 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* q, int Q
                                                            const float* __restrict__ fold, __half* __restrict__ a16,
                                                            float* __restrict__ rq, float* __restrict__ anorm,
                                                            uint32_t* __restrict__ thr_global,
-                                                           uint32_t* __restrict__ rowcnt, int nlists,
-                                                           float* __restrict__ gmax,
                                                            uint32_t* __restrict__ rowflag,
                                                            int32_t* __restrict__ counters, const int x_on,
                                                            const xchg::Exchange xc) {
@@ -158,8 +179,6 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* q, int Q
   r = ptx::warp_sum(r);
   n2 = ptx::warp_sum(n2);
   amax = ptx::warp_max(amax);
-  for (int l = lane; l < nlists; l += 32) rowcnt[(size_t)i * nlists + l] = 0;
-  for (int l = lane; l < nlists * 16; l += 32) gmax[(size_t)i * nlists * 16 + l] = -INFINITY;
   if (lane == 0) {
     rq[i] = r;
     anorm[i] = sqrtf(n2);
@@ -190,6 +209,7 @@ struct RescoreParams {
   int32_t* fallback_rows; // (Q)
   int x_on;               // sharded search: queries from the exchange's q_all, lists to the queries' owners
   xchg::Exchange x;
+  PiecePlan plan;         // which of the row's nlists slots the tensor-core pass wrote
 };
 
 // Where a query's top-k row goes.  Single GPU: row qi of the caller's (Q,k) outputs.  Sharded search: slot
@@ -267,6 +287,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   const bool overflow = p.counters[1] != 0 || p.gstat[1] != 0.f;
   bool certified = !overflow && p.rowflag[qi] == 0;
   const float tau = ptx::ordered_to_float(p.thr_global[qi]);
+  const int nl_valid = min(p.nlists, 4 * plan_pieces_of_row(p.plan, qi));   // the sub-lists written for this row
   float cv = -INFINITY;
   uint32_t cidx = 0xffffffffu;
   uint2* wb = wbuf[warp];
@@ -284,8 +305,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     // A tighter start: the row's group maxima belong to pairwise distinct gallery items, so the
     // 32nd largest of them (here: its ordered-integer image to 8 significant bits, found MSB
     // first) also bounds the 32nd best -- with ~40 instead of ~300 items above it.
-    const int nval = p.nlists * 16;
-    const float* gmp = p.gmax + (size_t)qi * nval;
+    const int nval = nl_valid * 16;
+    const float* gmp = p.gmax + (size_t)qi * p.nlists * 16;
     uint32_t key[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -363,14 +384,14 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     }
     __syncwarp();
   };
-  for (int l0 = 0; l0 < p.nlists && certified; l0 += 32) {
+  for (int l0 = 0; l0 < nl_valid && certified; l0 += 32) {
     const int my_l = l0 + lane;
-    uint32_t my_n = my_l < p.nlists ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
+    uint32_t my_n = my_l < nl_valid ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
     if (__any_sync(ptx::FULL_MASK, my_n > (uint32_t)capq)) {
       certified = false;
       break;
     }
-    const int nl = min(32, p.nlists - l0);            // a multiple of RS_SUBL = 4 (4 sub-lists per piece)
+    const int nl = min(32, nl_valid - l0);            // a multiple of RS_SUBL = 4 (4 sub-lists per piece)
     for (int j0 = 0; j0 < nl; j0 += RS_SUBL) {       // RS_SUBL sub-lists per round, 32 quads of each
       int n4[RS_SUBL];
       int nmax = 0;
@@ -816,6 +837,7 @@ struct RankResolveParams {
   const float* gstat;
   const int32_t* target;
   int Q, G, nlists, CAP;
+  PiecePlan plan;
   int32_t* out_rank;
   float* out_margin;         // optional
   int32_t* counters;         // [0] rows for the exhaustive kernel, [1] query overflow flag
@@ -875,12 +897,13 @@ __global__ void __launch_bounds__(256) rank_resolve_kernel(const RankResolvePara
     fill = 0;
     __syncwarp();
   };
-  for (int l0 = 0; l0 < p.nlists && ok; l0 += 32) {
+  const int nl_valid = min(p.nlists, 4 * plan_pieces_of_row(p.plan, qi));
+  for (int l0 = 0; l0 < nl_valid && ok; l0 += 32) {
     const int my_l = l0 + lane;
-    const uint32_t my_n = my_l < p.nlists ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
-    total += my_l < p.nlists ? p.above[(size_t)qi * p.nlists + my_l] : 0;
+    const uint32_t my_n = my_l < nl_valid ? p.rowcnt[(size_t)qi * p.nlists + my_l] : 0u;
+    total += my_l < nl_valid ? p.above[(size_t)qi * p.nlists + my_l] : 0;
     if (__any_sync(ptx::FULL_MASK, my_n > (uint32_t)capq)) ok = false;
-    const int nl = min(32, p.nlists - l0);
+    const int nl = min(32, nl_valid - l0);
     for (int j = 0; j < nl && ok; ++j) {
       const int n = (int)__shfl_sync(ptx::FULL_MASK, my_n, j);
       const uint4* lp = rowq + (size_t)(l0 + j) * capq;

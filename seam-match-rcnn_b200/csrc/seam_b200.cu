@@ -76,6 +76,7 @@ struct ProfileScope {
   }
 };
 
+static_assert(exact::PLAN_MAX_GRID == score::MAX_GRID, "the re-score kernels carry a copy of the scorer's CTA ranges");
 static thread_local char g_create_err[256] = "";
 
 static unsigned int* g_watchdog_host[64] = {};
@@ -754,8 +755,7 @@ static int score_topk_impl(seam_handle* h, const xchg::Exchange* x, const float*
 
   {
     ProfileScope prof(h, SEAM_KERNEL_PREP_QUERIES, stream);
-    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt,
-                                                               s.P * score::NQ, gmax, rowflag, counters, x_on, xe);
+    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowflag, counters, x_on, xe);
     SEAM_LAUNCHED(h, "prep_queries_kernel");
   }
 
@@ -829,6 +829,9 @@ static int score_topk_impl(seam_handle* h, const xchg::Exchange* x, const float*
   rp.fallback_rows = frows;
   rp.x_on = x_on;
   rp.x = xe;
+  rp.plan.ntiles_n = s.ntiles_n;
+  rp.plan.nb = s.grid;
+  for (int b = 0; b <= s.grid; ++b) rp.plan.tb[b] = s.tb[b];
   {
     ProfileScope prof(h, SEAM_KERNEL_RESCORE, stream);
     exact::rescore_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(rp);
@@ -864,6 +867,19 @@ int seam_score_topk(seam_handle* h, const float* q, int Q, const float* g, const
                     int32_t* out_idx, int32_t* stats, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!h) return SEAM_ERR_BAD_ARG;
   return score_topk_impl(h, nullptr, q, Q, g, g16, cg, gstat, G, index_offset, k, out_score, out_margin, out_idx, stats,
+                         workspace, workspace_bytes, stream_);
+}
+
+int seam_search(seam_handle* h, const float* seq, const uint8_t* mask, const int32_t* lens, int Tmax, int Q,
+                int64_t frame_stride, int64_t track_stride, float* q_out, const float* g, const void* g16, const float* cg,
+                const float* gstat, int G, int index_offset, int k, float* out_score, float* out_margin, int32_t* out_idx,
+                int32_t* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!h) return SEAM_ERR_BAD_ARG;
+  if (!q_out && Q > 0) return fail(h, SEAM_ERR_BAD_ARG, "seam_search: q_out is null");
+  int rc = aggregate_impl(h, nullptr, 0, 0, seq, mask, lens, Tmax, Q, frame_stride, track_stride, q_out, nullptr,
+                          static_cast<cudaStream_t>(stream_), "seam_search");
+  if (rc != SEAM_OK) return rc;
+  return score_topk_impl(h, nullptr, q_out, Q, g, g16, cg, gstat, G, index_offset, k, out_score, out_margin, out_idx, stats,
                          workspace, workspace_bytes, stream_);
 }
 
@@ -1019,8 +1035,7 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
 
   xchg::Exchange no_x;
   memset(&no_x, 0, sizeof(no_x));
-  exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowcnt, nlists, gmax,
-                                                             rowflag, counters, 0, no_x);
+  exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowflag, counters, 0, no_x);
   SEAM_LAUNCHED(h, "prep_queries_kernel");
   exact::rank_prep_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, g, target, h->fold, rq, anorm, gstat, lo, hi, dtarget,
                                                           above, nlists);
@@ -1076,6 +1091,9 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
   rp.out_margin = out_margin;
   rp.counters = counters;
   rp.fallback_rows = frows;
+  rp.plan.ntiles_n = s.ntiles_n;
+  rp.plan.nb = s.grid;
+  for (int b = 0; b <= s.grid; ++b) rp.plan.tb[b] = s.tb[b];
   exact::rank_resolve_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(rp);
   SEAM_LAUNCHED(h, "rank_resolve_kernel");
   exact::rank_of_target_kernel<<<2 * h->num_sms, 256, 0, stream>>>(q, Q, g, G, target, h->fold, counters, frows, out_rank,

@@ -440,6 +440,29 @@ class SeamEngine:
             return sc, mg, ix, stats
         return sc, mg, ix
 
+    def search(self, seq: torch.Tensor, mask, gallery: PreparedGallery, k: int, lens=None, return_stats: bool = False):
+        """Tracks -> (descriptors x3_1b (Q,256), scores (Q,k), margins (Q,k), idx (Q,k) int32) in one library call
+        (``seam_search``): same results as ``aggregate`` + ``score_topk``."""
+        seq, m8, l32, Tmax, Q = self._tracks(seq, mask, lens)
+        gallery = self._fresh(gallery)
+        G, k = gallery.G, int(k)
+        nbytes = int(self._lib.seam_score_workspace_bytes(self._h, Q, G, k))
+        if nbytes > SCORE_WS_LIMIT:                      # very large evaluations: the slab path of score_topk
+            q = self.aggregate(seq, mask, lens=lens)
+            return (q,) + tuple(self.score_topk(q, gallery, k, return_stats=return_stats))
+        q = torch.empty((Q, D_MODEL), dtype=torch.float32, device=self.device)
+        sc = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        mg = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        ix = torch.empty((Q, k), dtype=torch.int32, device=self.device)
+        stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        ws = self._workspace("score", nbytes)
+        self._check(self._lib.seam_search(self._h, seq.data_ptr() if Q else 0, _ptr(m8), _ptr(l32), Tmax, Q, seq.stride(0),
+                                          seq.stride(1), q.data_ptr(), gallery.g.data_ptr(), gallery.g16.data_ptr(),
+                                          gallery.cg.data_ptr(), gallery.gstat.data_ptr(), G, int(gallery.index_offset), k,
+                                          sc.data_ptr(), mg.data_ptr(), ix.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), self._stream()))
+        return (q, sc, mg, ix, stats) if return_stats else (q, sc, mg, ix)
+
     def score_plan(self, Q: int, G: int) -> Dict[str, int]:
         """Work decomposition + workspace layout seam_score_topk will use for (Q,G)."""
         out = (C.c_int64 * 14)()

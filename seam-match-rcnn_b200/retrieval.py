@@ -48,14 +48,53 @@ def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------
+# host placement
+# ----------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(device) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (Linux sysfs), so that the pinned host
+    buffers it allocates afterwards are first-touched on that node: on a two-socket 8-GPU box a rank whose buffers
+    live on the other socket moves its tracks over the inter-socket link and gets a fraction of its PCIe bandwidth.
+    Returns the node, or None when it cannot be determined (nothing is changed then).  Call it before allocating
+    pinned memory; one process per GPU."""
+    import os
+    try:
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        bus = torch.cuda.get_device_properties(idx).pci_bus_id if hasattr(torch.cuda.get_device_properties(idx), "pci_bus_id") else None
+        if bus is None:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:                                        # noqa: BLE001 -- placement is an optimisation, never an error
+        return None
+
+
+# ----------------------------------------------------------------------------------------
 # single GPU
 # ----------------------------------------------------------------------------------------
 def search(engine: SeamEngine, seq: torch.Tensor, mask: Optional[torch.Tensor], gallery, k: int = 20):
     """aggregation -> scorer -> top-k for all tracks.  Returns (scores, margins, idx int32)."""
     if not isinstance(gallery, PreparedGallery):
         gallery = engine.prepare_gallery(gallery)
-    q = engine.aggregate(seq, mask)
-    return engine.score_topk(q, gallery, k)
+    return engine.search(seq, mask, gallery, k)[1:]
 
 
 # ----------------------------------------------------------------------------------------
