@@ -124,6 +124,11 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
   u64 r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -292,7 +297,7 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
     const long long f = first0 + u;
     if (f < p.Q) n_cta += (p.Q - f + stride - 1) / stride;
   }
-#ifdef SEAM_AGG_DIAG_NO_PUBLISH     // developer diagnostic (wrong results): streaming pass alone
+#if defined(SEAM_AGG_DIAG_NO_PUBLISH) || defined(SEAM_AGG_GDIAG)    // developer diagnostic (wrong results): streaming pass alone
   const int nbatch = 0;
 #else
   const int nbatch = (int)((n_cta + NB - 1) / NB);
@@ -791,7 +796,9 @@ constexpr int GREGS_P = 224, GREGS_H = 56;
 
 template <int GW>
 struct alignas(16) GroupSmem {
-  float scal[FB * GW][4];              // per frame: a, d -> p, b, c -> q
+  float ad[FB * GW / 2][4];            // per pair of frames: a_even, a_odd, d_even -> p_even, d_odd -> p_odd
+  float bc[FB * GW / 2][4];            // b_even, b_odd, c_even, c_odd (zero for frames past the track's end)
+  float pq[FB * GW][4];                // per frame: p, p, q, q
   float part[GW][2 * D];               // per warp: partial pooled | partial r
   float red_max[GW];
   float red_sum[GW];
@@ -810,7 +817,8 @@ template <int GW>
 constexpr size_t group_smem_bytes() { return 1024 + fused_bytes<false>() + sizeof(GSmem<GW>); }
 
 template <int GW>
-__global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(const Params p) {
+__global__ void __launch_bounds__(GTHREADS, 1)
+aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Params p) {
   constexpr int GROUPS_PER_CTA = GWARPS / GW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -866,7 +874,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
       else ptx::mbar_arrive(bar);
     }
     __syncwarp();
-    if (lane < nw) {
+    if (p.use_tm && nw == FB) {
+      // a full block: frames FB wg + 1 .. FB wg + 16 of this track as ONE box {256 channels, 1 track, 16 frames}
+      // (the per-frame loop below is ~10 instructions and a branch per frame: uniform-datapath copies issued lane by lane)
+      if (ptx::elect_one()) ptx::tma_load_3d_hint(xs, &tmSeq, bar, 0, (int)track, FB * wg + 1, pol);
+      __syncwarp();
+    } else if (lane < nw) {
       const float* src = p.seq + (long long)(FB * wg + lane + 1) * p.frame_stride + track * p.track_stride;
 #ifdef SEAM_AGG_NO_HINT
       ptx::bulk_load_1d(xs + (size_t)lane * D, src, D * 4, bar);
@@ -898,6 +911,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
     const int comp = lane & 3;
     const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
                          : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
+    // where this lane's butterfly total (component comp of frame SF0 + t0) goes: the T x T loops read PAIRS of frames
+    const int SF0 = FB * wg + ((lane >> 2) & 3);
+    float* const sc_dst = (comp < 2 ? &gs.ad[0][0] : &gs.bc[0][0]) + (SF0 >> 1) * 4 + ((comp & 1) << 1) + (SF0 & 1);
 
 #ifndef SEAM_AGG_HELPER_INIT
     load_m_tmem<GWARPS + HELPER_WARPS, 2>(p, meta, warp, lane);   // while the first frames are in flight
@@ -924,68 +940,104 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
           acc[4 * u + 3] = dot8(x[t], ug);
         }
         const float tot = treduce<16>(acc, lane);
-        if (lane < 16) gs.scal[FB * wg + t0 + (lane >> 2)][comp] = tot + my_const;
+        // frame F = FB wg + t0 + (lane >> 2): a, d -> ad[F / 2][F % 2 (+ 2)], b, c -> bc[...], zero past the track's end
+        if (lane < 16) sc_dst[2 * t0] = (comp < 2 || SF0 + t0 < len) ? tot + my_const : 0.f;
       }
       // the buffer is free again: fetch this warp's block of the group's next track
       const int len_next = track_len(track + stride);
       __syncwarp();
       issue(track + stride, len_next);
+#if defined(SEAM_AGG_GDIAG) && SEAM_AGG_GDIAG == 1      // developer diagnostic (wrong results): frames -> registers + dots only
+      if (len == -5) p.out[track] = x[3].a + x[15].d;
+      len = len_next;
+      continue;
+#endif
       ptx::named_bar_sync(bar_id, GW * 32);                       // #1 all scalars of the track are visible
 
-      // ---- attention over the track's frames: lane = (frame f of my block, half of the j / t range)
+      // ---- attention over the track's frames: lane = (frame f of my block, half of the j / t range).  The loops
+      // take two frames per step ({b_e, b_o, c_e, c_o}: one 16-byte load, one packed add, one packed fma) into two
+      // independent accumulators; the 1/T factor is applied once at the end.
       const int f = lane & 15, half = lane >> 4;
       const int F = FB * wg + f;
       const bool valid = F < len;
+      const int npairs = (len + 1) >> 1;
       const float inv_len = len > 0 ? 1.f / (float)len : 0.f;
-      float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) sc = *reinterpret_cast<const float4*>(&gs.scal[F][0]);   // a, d, b, c of my frame
-      float sum = 0.f;
-      if (len > 1) {
-        for (int j = half; j < len; j += 2) {
-          const float2 bc = *reinterpret_cast<const float2*>(&gs.scal[j][2]);
-          sum = fmaf(fmaxf(sc.x + bc.x, 0.f) * inv_len, bc.y, sum);
+      const float a_f = gs.ad[F >> 1][F & 1], d_f = gs.ad[F >> 1][2 + (F & 1)], b_f = gs.bc[F >> 1][F & 1];
+      auto interact = [&](const float own, const float (*tab)[4]) -> float {   // sum_j relu(own + tab.x_j) * tab.y_j
+        const u64 o2 = pk(own, own);
+        u64 acc_a = 0ull, acc_b = 0ull;
+        int jj = half;
+        for (; jj + 2 < npairs; jj += 4) {
+          const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(&tab[jj][0]);
+          const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(&tab[jj + 2][0]);
+          float s0, s1, s2, s3;
+          upk(add2(o2, v0.x), s0, s1);
+          upk(add2(o2, v1.x), s2, s3);
+          acc_a = fma2(pk(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), v0.y, acc_a);
+          acc_b = fma2(pk(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), v1.y, acc_b);
         }
-      }
-      sum += __shfl_xor_sync(ptx::FULL_MASK, sum, 16);
-      const float s_t = valid ? sc.y + sum + c_s : -INFINITY;
+        if (jj < npairs) {
+          const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(&tab[jj][0]);
+          float s0, s1;
+          upk(add2(o2, v0.x), s0, s1);
+          acc_a = fma2(pk(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), v0.y, acc_a);
+        }
+        float lo, hi, lo2, hi2;
+        upk(acc_a, lo, hi);
+        upk(acc_b, lo2, hi2);
+        float r = (lo + hi) + (lo2 + hi2);
+        r += __shfl_xor_sync(ptx::FULL_MASK, r, 16);
+        return r * inv_len;
+      };
+      const float sum = len > 1 ? interact(a_f, gs.bc) : 0.f;
+      const float s_t = valid ? d_f + sum + c_s : -INFINITY;
+      // softmax over the track with ONE barrier: every warp publishes the maximum of its block and the sum of
+      // exp(s - its maximum); m = max_w m_w, z = sum_w z_w exp(m_w - m), p_t = exp(s_t - m) / z
       const float m_w = ptx::warp_max(s_t);
-      if (lane == 0) gs.red_max[wg] = m_w;
-      ptx::named_bar_sync(bar_id, GW * 32);                       // #2 (also: nobody reads b, c, d any more)
+      const float z_w = ptx::warp_sum(half == 0 && valid ? expf(s_t - m_w) : 0.f);
+      if (lane == 0) {
+        gs.red_max[wg] = m_w;
+        gs.red_sum[wg] = z_w;
+      }
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #2 (also: nobody reads d any more)
       float m = gs.red_max[0];
 #pragma unroll
       for (int w = 1; w < GW; ++w) m = fmaxf(m, gs.red_max[w]);
-      const float e_t = valid ? expf(s_t - m) : 0.f;
-      const float z_w = ptx::warp_sum(half == 0 ? e_t : 0.f);
-      if (lane == 0) gs.red_sum[wg] = z_w;
-      ptx::named_bar_sync(bar_id, GW * 32);                       // #3
-      float z = gs.red_sum[0];
+      float z = 0.f;
 #pragma unroll
-      for (int w = 1; w < GW; ++w) z += gs.red_sum[w];
-      const float p_t = valid ? e_t / z : 0.f;
-      if (half == 0) gs.scal[F][1] = p_t;
+      for (int w = 0; w < GW; ++w) {
+        const float mw = gs.red_max[w];
+        if (mw > -INFINITY) z += gs.red_sum[w] * expf(mw - m);     // a warp without frames of this track: (-inf, 0)
+      }
+      const float p_t = valid ? expf(s_t - m) / z : 0.f;
+      if (half == 0) gs.ad[F >> 1][2 + (F & 1)] = p_t;
 #if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3)
       if (p.att && half == 0 && F < Tmax) p.att[(size_t)track * Tmax + F] = p_t;
 #endif
       ptx::named_bar_sync(bar_id, GW * 32);                       // #4 all p_t are visible
-      float q_j = 0.f;
-      if (len > 1 && valid) {
-        for (int t = half; t < len; t += 2) {
-          const float2 ap = *reinterpret_cast<const float2*>(&gs.scal[t][0]);
-          q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
-        }
-      }
-      q_j += __shfl_xor_sync(ptx::FULL_MASK, q_j, 16);
+      float q_j = len > 1 ? interact(b_f, gs.ad) : 0.f;            // sum_t relu(b_j + a_t) p_t / T
+      if (!valid) q_j = 0.f;
       const float qsum_w = ptx::warp_sum(half == 0 ? q_j : 0.f);
+      if (half == 0) *reinterpret_cast<float4*>(&gs.pq[F][0]) = make_float4(p_t, p_t, q_j, q_j);
+      __syncwarp();
 
-      // ---- partial weighted sums over my frames, 8 channels per lane
+#if defined(SEAM_AGG_GDIAG) && SEAM_AGG_GDIAG == 2      // developer diagnostic (wrong results): ... + attention, no weighted sums
+      if (len == -5) p.out[track] = x[3].a + x[15].d;
+      len = len_next;
+      continue;
+#endif
+      // ---- partial weighted sums over my frames, 8 channels per lane.  {p, p}, {q, q} come from shared memory (one
+      // broadcast load per frame, four in flight); frames past the block's end are zero in registers and need no guard.
       Vec8 pov = zero_vec8(), rv = zero_vec8();
 #pragma unroll
-      for (int t = 0; t < FB; ++t) {
-        const float pt = __shfl_sync(ptx::FULL_MASK, p_t, t);
-        const float qt = __shfl_sync(ptx::FULL_MASK, q_j, t);
-        if (t < nw) {
-          fma8(pov, pk(pt, pt), x[t]);
-          fma8(rv, pk(qt, qt), x[t]);
+      for (int t0 = 0; t0 < FB; t0 += 4) {
+        ulonglong2 w2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w2[u] = *reinterpret_cast<const ulonglong2*>(&gs.pq[FB * wg + t0 + u][0]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          fma8(pov, w2[u].x, x[t0 + u]);
+          fma8(rv, w2[u].y, x[t0 + u]);
         }
       }
       float4 po0, po1, r0, r1;
@@ -1070,6 +1122,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) aggregate_fused_group_kernel(cons
   fused_teardown(fz, warp, GWARPS);
   if (p.x_on && p.x_last) xchg::signal_all(p.x, xchg::KIND_Q, xstep);
 }
+
 
 }  // namespace aggf
 }  // namespace seam

@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* q, int Q
                                                            float* __restrict__ rq, float* __restrict__ anorm,
                                                            uint32_t* __restrict__ thr_global,
                                                            uint32_t* __restrict__ rowflag,
-                                                           int32_t* __restrict__ counters, const int x_on,
+                                                           int32_t* __restrict__ counters,
+                                                           int32_t* __restrict__ xdone, const int x_on,
                                                            const xchg::Exchange xc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + warp;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* q, int Q
     anorm[i] = sqrtf(n2);
     thr_global[i] = ptx::float_to_ordered(-INFINITY);
     rowflag[i] = 0;
+    if (xdone) xdone[i] = 0;            // exhaustive kernel: slices finished per uncertified row
     if (!(amax < FP16_MAX)) atomicExch(counters + 1, 1);
   }
 }
@@ -509,15 +511,25 @@ struct ExactParams {
   float* out_score;
   float* out_margin;
   int32_t* out_idx;
+  float* part_d;          // (max(grid, Q), 32) per-slice lists of a row split over several CTAs (null: never split)
+  int32_t* part_i;
+  int32_t* done;          // (Q) slices finished per listed row; zero on entry (prep_queries_kernel), zero again on exit
   int x_on;               // sharded search: see RescoreParams; this is the step's last list-writing kernel: it signals
   xchg::Exchange x;
 };
 
-// CTA (8 warps) per row: each warp scans every 8th gallery item keeping a sorted best-32 in
-// its lanes, the eight lists are merged through shared memory.
+constexpr int EXACT_MIN_SLICE = 128;   // gallery rows per slice at least (16 per warp: 4 rounds of 4)
+
+// CTA (8 warps) per (row, gallery slice): each warp scans its share of the slice four items at a time (eight 16-byte
+// loads per lane in flight, one transposing butterfly for the eight partial sums) keeping a sorted best-32 in its
+// lanes; the eight lists are merged through shared memory.  A handful of uncertified rows must not cost a gallery
+// sweep by ONE CTA each (15,000 items: 0.87 ms for a single row, four times the whole step): with fewer rows than CTAs
+// a row's gallery is cut into S = grid / rows slices, every slice's list goes to global memory and the CTA that
+// finishes a row's last slice merges them.  The result is independent of S: (margin desc, index asc) is a total order.
 __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
   __shared__ float sd[8][32];
   __shared__ int si[8][32];
+  __shared__ int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrows = p.count ? *p.count : p.Q;
   const uint32_t xstep = p.x_on ? xchg::current_step(p.x) : 0u;
@@ -525,30 +537,13 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
   const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
   const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
   const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
-  for (int e = blockIdx.x; e < nrows; e += gridDim.x) {
-    const int qi = p.count ? p.rows[e] : e;
-    const Slice qs = load_slice(qbase + (size_t)qi * 256, lane);
-    float cd = -INFINITY;
-    int cidx = INT_MAX;
-    for (int j = warp; j < p.G; j += 8) {
-      float l0, l1;
-      pair_logits(qs, p.g + (size_t)j * 256, w0, w1, b0, b1, lane, l0, l1);
-      const float d = l1 - l0;
-      const float wd = __shfl_sync(ptx::FULL_MASK, cd, 31);
-      const int wi = __shfl_sync(ptx::FULL_MASK, cidx, 31);
-      if (wsort::ranks_before(d, j, wd, wi)) {   // warp-uniform
-        const int pos = __popc(__ballot_sync(ptx::FULL_MASK, wsort::ranks_before(cd, cidx, d, j)));
-        const float ud = __shfl_up_sync(ptx::FULL_MASK, cd, 1);
-        const int ui = __shfl_up_sync(ptx::FULL_MASK, cidx, 1);
-        if (lane > pos) {
-          cd = ud;
-          cidx = ui;
-        } else if (lane == pos) {
-          cd = d;
-          cidx = j;
-        }
-      }
-    }
+  int S = 1;
+  if (p.part_d && nrows > 0 && nrows < (int)gridDim.x) S = max(1, min((int)gridDim.x / nrows, p.G / EXACT_MIN_SLICE));
+  const long long units = (long long)nrows * S;
+  float cd;
+  int cidx;
+  // the eight warps' sorted lists -> one sorted best-32 in warp 0
+  auto cta_merge = [&]() {
     sd[warp][lane] = cd;
     si[warp][lane] = cidx;
     __syncthreads();
@@ -563,28 +558,97 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
         }
         wsort::merge32_rank(cd, cidx, dummy, lane);
       }
-      // scores of the winners
-      float my_sc = 0.f;
-      for (int c = 0; c < p.k; ++c) {
-        const int idx = __shfl_sync(ptx::FULL_MASK, cidx, c);
-        if (idx == INT_MAX) continue;
-        float l0, l1;
-        pair_logits(qs, p.g + (size_t)idx * 256, w0, w1, b0, b1, lane, l0, l1);
-        if (lane == c) my_sc = softmax1(l0, l1);
+    }
+  };
+  auto write_row = [&](int qi) {                 // warp 0
+    if (lane < p.k) {
+      const TopkDest dst = topk_dest(p.x_on, p.x, xstep, qi, p.k, p.out_score, p.out_margin, p.out_idx);
+      const bool ok = cidx != INT_MAX;
+      // softmax(l0, l1)[1] as a function of d = l1 - l0: bit-identical to softmax1(l0, l1) (rescore_kernel)
+      if (dst.score) dst.score[lane] = ok ? softmax1(0.f, cd) : 0.f;
+      dst.margin[lane] = cd;
+      dst.idx[lane] = ok ? cidx + p.index_offset : -1;
+    }
+  };
+  for (long long e = blockIdx.x; e < units; e += gridDim.x) {
+    const int r = (int)(e / S), sl = (int)(e - (long long)r * S);
+    const int qi = p.count ? p.rows[r] : r;
+    const int j_lo = (int)((long long)p.G * sl / S), j_hi = (int)((long long)p.G * (sl + 1) / S);
+    const Slice qs = load_slice(qbase + (size_t)qi * 256, lane);
+    cd = -INFINITY;
+    cidx = INT_MAX;
+    for (int j0 = j_lo + 4 * warp; j0 < j_hi; j0 += 32) {
+      Slice gs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) gs[u] = load_slice(p.g + (size_t)min(j0 + u, j_hi - 1) * 256, lane);
+      float part[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sqdiff_dot2(qs, gs[u], w0, w1, part[2 * u], part[2 * u + 1]);
+      const float tot = ptx::treduce<8>(part, lane);   // lane l: total of part[l % 8] -- the association of warp_sum_b
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float l0 = __shfl_sync(ptx::FULL_MASK, tot, 2 * u) + b0;
+        const float l1 = __shfl_sync(ptx::FULL_MASK, tot, 2 * u + 1) + b1;
+        const float d = l1 - l0;
+        const int j = j0 + u;
+        const float wd = __shfl_sync(ptx::FULL_MASK, cd, 31);
+        const int wi = __shfl_sync(ptx::FULL_MASK, cidx, 31);
+        if (j < j_hi && wsort::ranks_before(d, j, wd, wi)) {   // warp-uniform
+          const int pos = __popc(__ballot_sync(ptx::FULL_MASK, wsort::ranks_before(cd, cidx, d, j)));
+          const float ud = __shfl_up_sync(ptx::FULL_MASK, cd, 1);
+          const int ui = __shfl_up_sync(ptx::FULL_MASK, cidx, 1);
+          if (lane > pos) {
+            cd = ud;
+            cidx = ui;
+          } else if (lane == pos) {
+            cd = d;
+            cidx = j;
+          }
+        }
       }
-      if (lane < p.k) {
-        const TopkDest dst = topk_dest(p.x_on, p.x, xstep, qi, p.k, p.out_score, p.out_margin, p.out_idx);
-        const bool ok = cidx != INT_MAX;
-        if (dst.score) dst.score[lane] = ok ? my_sc : 0.f;
-        dst.margin[lane] = cd;
-        dst.idx[lane] = ok ? cidx + p.index_offset : -1;
+    }
+    cta_merge();
+    if (S == 1) {
+      if (warp == 0) write_row(qi);
+      __syncthreads();
+      continue;
+    }
+    // this slice's list -> global; the CTA that completes the row merges the S lists
+    if (warp == 0) {
+      __stcg(p.part_d + (size_t)e * 32 + lane, cd);
+      __stcg(p.part_i + (size_t)e * 32 + lane, cidx);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) s_last = atomicAdd(p.done + r, 1) == S - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      cd = -INFINITY;
+      cidx = INT_MAX;
+      float dummy = 0.f;
+      for (int s2 = warp; s2 < S; s2 += 8) {
+        const size_t o = ((size_t)r * S + s2) * 32 + (31 - lane);
+        const float od = __ldcg(p.part_d + o);
+        const int oi = __ldcg(p.part_i + o);
+        if (wsort::ranks_before(od, oi, cd, cidx)) {
+          cd = od;
+          cidx = oi;
+        }
+        wsort::merge32_rank(cd, cidx, dummy, lane);
+      }
+      __syncthreads();                       // sd / si of the slice merge are free again
+      cta_merge();
+      if (warp == 0) {
+        write_row(qi);
+        if (lane == 0) p.done[r] = 0;        // as found: the next call may use any number of slices
       }
     }
     __syncthreads();
   }
   if (p.x_on) {          // every list row of this step (re-score kernel before: complete at its end; this one now) is on its way
     __syncthreads();
-    xchg::signal_all(p.x, xchg::KIND_L, xstep, (int)blockIdx.x < nrows);
+    xchg::signal_all(p.x, xchg::KIND_L, xstep, (long long)blockIdx.x < units);
   }
 }
 

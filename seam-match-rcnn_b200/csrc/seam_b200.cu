@@ -126,35 +126,39 @@ struct DeviceGuard {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Full tracks / full frame blocks are fetched with one 3-D tensor-map copy: box {256, 1 track, frames} over seq viewed as
+// (1+Tmax, Q, 256) with the caller's strides.  Returns whether the map is usable.
+static int encode_seq_map(seam_handle* h, const aggf::Params& p, int box_frames, CUtensorMap* tm) {
+  memset(tm, 0, sizeof(*tm));
+  if (!p.seq || p.Q <= 0 || (p.track_stride * 4) % 16 != 0 || (p.frame_stride * 4) % 16 != 0 || p.track_stride < 256 ||
+      p.frame_stride < 256 || box_frames > p.Tmax)
+    return 0;
+  const cuuint64_t dims[3] = {256, (cuuint64_t)p.Q, (cuuint64_t)(1 + p.Tmax)};
+  const cuuint64_t strides[2] = {(cuuint64_t)p.track_stride * 4, (cuuint64_t)p.frame_stride * 4};
+  const cuuint32_t box[3] = {256, 1, (cuuint32_t)box_frames};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.seq), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int TR>
 static void launch_aggregate_warp(seam_handle* h, aggf::Params& p, int num_sms, cudaStream_t stream) {   // num_sms = CTA cap
   constexpr int NW = aggf::Cfg<TR>::NW;
   const int want = (p.Q + NW - 1) / NW;
   const int grid = want < num_sms ? want : num_sms;
-  // full tracks (len == Tmax == TR) are fetched with one 3-D tensor-map copy: box {256, 1 track, TR frames} over
-  // seq viewed as (1+Tmax, Q, 256) with the caller's strides
   CUtensorMap tm;
-  memset(&tm, 0, sizeof(tm));
-  p.use_tm = 0;
-  if (p.Tmax == TR && p.seq && (p.track_stride * 4) % 16 == 0 && (p.frame_stride * 4) % 16 == 0 &&
-      p.track_stride >= 256 && p.frame_stride >= 256) {
-    const cuuint64_t dims[3] = {256, (cuuint64_t)p.Q, (cuuint64_t)(1 + p.Tmax)};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.track_stride * 4, (cuuint64_t)p.frame_stride * 4};
-    const cuuint32_t box[3] = {256, 1, (cuuint32_t)TR};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (h->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.seq), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-      p.use_tm = 1;
-  }
+  p.use_tm = p.Tmax == TR ? encode_seq_map(h, p, TR, &tm) : (memset(&tm, 0, sizeof(tm)), 0);
   aggf::aggregate_fused_warp_kernel<TR><<<grid, aggf::warp_threads<TR>(), aggf::warp_smem_bytes<TR>(), stream>>>(tm, p);
 }
 template <int GW>
-static void launch_aggregate_group(const aggf::Params& p, int num_sms, cudaStream_t stream) {
+static void launch_aggregate_group(seam_handle* h, aggf::Params& p, int num_sms, cudaStream_t stream) {
   constexpr int GPC = aggf::GWARPS / GW;
   const int want = (p.Q + GPC - 1) / GPC;
   const int grid = want < num_sms ? want : num_sms;
-  aggf::aggregate_fused_group_kernel<GW><<<grid, aggf::GTHREADS, aggf::group_smem_bytes<GW>(), stream>>>(p);
+  CUtensorMap tm;
+  p.use_tm = encode_seq_map(h, p, aggf::FB, &tm);
+  aggf::aggregate_fused_group_kernel<GW><<<grid, aggf::GTHREADS, aggf::group_smem_bytes<GW>(), stream>>>(tm, p);
 }
 
 static int import_exchange(seam_handle* h, const seam_exchange* x, xchg::Exchange* e, const char* who) {
@@ -428,8 +432,8 @@ static int aggregate_impl(seam_handle* h, const xchg::Exchange* x, int row0, int
   if (Tmax <= 4) launch_aggregate_warp<4>(h, p, cap, stream);
   else if (Tmax <= 10) launch_aggregate_warp<10>(h, p, cap, stream);
   else if (Tmax <= 16) launch_aggregate_warp<16>(h, p, cap, stream);
-  else if (Tmax <= 32) launch_aggregate_group<2>(p, cap, stream);   // two warps per track
-  else launch_aggregate_group<4>(p, cap, stream);                   // 33..64 frames: four warps per track
+  else if (Tmax <= 32) launch_aggregate_group<2>(h, p, cap, stream);   // two warps per track
+  else launch_aggregate_group<4>(h, p, cap, stream);                   // 33..64 frames: four warps per track
   SEAM_LAUNCHED(h, "aggregate kernel");
   return SEAM_OK;
 }
@@ -524,7 +528,7 @@ struct ScorePlan {
   int num_mtiles, ntiles_n, grid, P, CAP, nseed;
   int tb[score::MAX_GRID + 1];
   long long total_tiles;
-  size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_gmax, off_rowflag, off_rowbuf, off_cnt, off_rows, total;
+  size_t off_a16, off_rq, off_anorm, off_thr, off_rowcnt, off_gmax, off_rowflag, off_rowbuf, off_cnt, off_rows, off_xpart, off_xdone, total;
 };
 
 // The (query tile, gallery tile) grid is linearised query-major and cut into one contiguous
@@ -650,6 +654,10 @@ static ScorePlan plan_score(int num_sms, int Q, int G, int nseed_override = -1, 
   s.off_rowbuf = o;  o += align_up((size_t)Q * nlists * s.CAP * 8 + (size_t)s.CAP * 8, 256);   // + slack to align the base
   s.off_cnt = o;     o += 256;
   s.off_rows = o;    o += align_up((size_t)Q * 4, 256);
+  // exhaustive kernel: per-slice lists of rows split over several CTAs (units <= max(its grid, Q)), per-row counts
+  const size_t xunits = (size_t)(Q > 2 * num_sms ? Q : 2 * num_sms);
+  s.off_xpart = o;   o += align_up(xunits * 32 * 8, 256);
+  s.off_xdone = o;   o += align_up((size_t)Q * 4, 256);
   s.total = o;
   return s;
 }
@@ -752,10 +760,14 @@ static int score_topk_impl(seam_handle* h, const xchg::Exchange* x, const float*
       align_up(reinterpret_cast<uintptr_t>(ws + s.off_rowbuf), (size_t)s.CAP * 8));
   int32_t* counters = reinterpret_cast<int32_t*>(ws + s.off_cnt);
   int32_t* frows = reinterpret_cast<int32_t*>(ws + s.off_rows);
+  const size_t xunits = (size_t)(Q > 2 * h->num_sms ? Q : 2 * h->num_sms);
+  float* xpart_d = reinterpret_cast<float*>(ws + s.off_xpart);
+  int32_t* xpart_i = reinterpret_cast<int32_t*>(ws + s.off_xpart + xunits * 32 * 4);
+  int32_t* xdone = reinterpret_cast<int32_t*>(ws + s.off_xdone);
 
   {
     ProfileScope prof(h, SEAM_KERNEL_PREP_QUERIES, stream);
-    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowflag, counters, x_on, xe);
+    exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowflag, counters, xdone, x_on, xe);
     SEAM_LAUNCHED(h, "prep_queries_kernel");
   }
 
@@ -851,6 +863,9 @@ static int score_topk_impl(seam_handle* h, const xchg::Exchange* x, const float*
   ep.out_score = out_score;
   ep.out_margin = out_margin;
   ep.out_idx = out_idx;
+  ep.part_d = xpart_d;
+  ep.part_i = xpart_i;
+  ep.done = xdone;
   ep.x_on = x_on;
   ep.x = xe;
   {
@@ -1035,7 +1050,7 @@ int seam_rank_of_target_prepared(seam_handle* h, const float* q, int Q, const fl
 
   xchg::Exchange no_x;
   memset(&no_x, 0, sizeof(no_x));
-  exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowflag, counters, 0, no_x);
+  exact::prep_queries_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, h->fold, a16, rq, anorm, thr, rowflag, counters, nullptr, 0, no_x);
   SEAM_LAUNCHED(h, "prep_queries_kernel");
   exact::rank_prep_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(q, Q, g, target, h->fold, rq, anorm, gstat, lo, hi, dtarget,
                                                           above, nlists);

@@ -179,6 +179,36 @@ def test_topk_near_duplicates_take_exhaustive_path(weights, engine):
     assert_topk_matches(ix, mg, sc, so.logit_margin(x5), so.match_scores(x5), 20)
 
 
+def test_topk_few_uncertified_rows_are_split_over_ctas(weights, engine):
+    """A handful of rows with a crowd of near-ties at the top of a large gallery: the exhaustive kernel cuts each such
+    row's gallery into slices (one CTA each) and merges the slice lists -- same answer as the oracle, stable over
+    repeated calls (the per-row slice counters are left as found), for odd G and k up to 32."""
+    rs = np.random.RandomState(11)
+    Q, G = 200, 20011
+    q = torch.from_numpy(rs.randn(Q, 256).astype(np.float32))
+    g = torch.from_numpy(rs.randn(G, 256).astype(np.float32))
+    x5 = so.pair_logits(q, g, weights, chunk=64)
+    crowded = [3, 77, 199]
+    for n, i in enumerate(crowded):                        # 40 near-copies of the row's best item, spread over the gallery
+        best = int(so.logit_margin(x5)[i].argmax())
+        rows = torch.from_numpy(rs.choice(G, 40, replace=False))
+        rows = rows[rows != best]
+        g[rows] = g[best] + 1e-5 * torch.from_numpy(rs.randn(len(rows), 256).astype(np.float32))
+    x5 = so.pair_logits(q, g, weights, chunk=64)
+    gal = engine.prepare_gallery(g.to(DEV))
+    for k in (20, 32):
+        first = None
+        for _ in range(3):
+            sc, mg, ix, stats = engine.score_topk(q.to(DEV), gal, k, return_stats=True)
+            if k == 20:     # at k = 32 the window is full for every row: all rows take the exhaustive kernel, unsliced
+                assert 3 <= int(stats[0]) < 148, "expected a few uncertified rows (fewer than CTAs: the sliced path)"
+            assert_topk_matches(ix, mg, sc, so.logit_margin(x5), so.match_scores(x5), k)
+            if first is None:
+                first = (sc.clone(), mg.clone(), ix.clone())
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(first, (sc, mg, ix)))
+
+
 def test_topk_rising_gallery_overflows_candidate_lists(weights, engine):
     """A gallery whose margins rise with the row index makes nearly every new item beat the running
     bound: the per-thread candidate lists fill up, close, and the affected rows must be flagged and
