@@ -109,6 +109,14 @@ using ptx::treduce;
 #define SEAM_TL2(p, slot) do { } while (0)
 #endif
 
+// developer diagnostic (SEAM_AGG_PHASES builds; the attention output is sacrificed): clock64 deltas of producer warp 0
+// per phase of the long-track kernel's iteration, summed over its iterations, 16 x i64 per CTA in the att buffer
+#ifdef SEAM_AGG_PHASES
+#define SEAM_PH(i) do { if (warp == 0 && lane == 0) { const long long t_ = clock64(); s.phase[i] += t_ - ph_prev; ph_prev = t_; } } while (0)
+#else
+#define SEAM_PH(i) do { } while (0)
+#endif
+
 // ---- packed fp32 pairs (FFMA2 / FMUL2): the streaming pass is bound by instruction issue
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) {
@@ -812,6 +820,9 @@ struct GSmem {
   float x[GWARPS][FB][D];              // 8 x 16 KB
   GroupSmem<GW> g[GWARPS / GW];
   uint64_t bar[GWARPS];
+#ifdef SEAM_AGG_PHASES
+  long long phase[16];                 // developer diagnostic: cycles warp 0 spent in each phase of its iterations
+#endif
 };
 template <int GW>
 constexpr size_t group_smem_bytes() { return 1024 + fused_bytes<false>() + sizeof(GSmem<GW>); }
@@ -847,18 +858,31 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
   const long long first = first0 + grp;
   const uint64_t pol = ptx::policy_evict_first();
 
-  // length of a track (every warp of the group derives it on its own)
-  auto track_len = [&](long long track) -> int {
+  // length of a track (every warp of the group derives it on its own).  peek() only issues the (dependent) loads --
+  // one track ahead of their use, so that their latency hides behind the current track's dots -- and decode() turns
+  // the loaded words into the length.
+  auto peek = [&](long long track) -> uint32_t {
+    if (track >= p.Q) return 0u;
+    if (p.lens) return (uint32_t)p.lens[track];
+    if (p.mask) {
+      const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
+      const uint32_t m0 = lane <= Tmax ? m[lane] : 0u;
+      const uint32_t m1 = 32 + lane <= Tmax ? m[min(32 + lane, Tmax)] : 0u;
+      const uint32_t m2 = lane == 0 && Tmax >= 64 ? m[min(64, Tmax)] : 0u;
+      return m0 | (m1 << 8) | (m2 << 16);
+    }
+    return 0u;
+  };
+  auto decode = [&](long long track, uint32_t raw) -> int {
     if (track >= p.Q) return 0;
     int len;
     if (p.lens) {
-      len = p.lens[track];
+      len = (int)raw;
     } else if (p.mask) {
       // first nonzero of the mask row ends the track; row 0 is the dummy (models/match_head.py:136-139)
-      const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
-      const uint32_t b0 = __ballot_sync(ptx::FULL_MASK, lane <= Tmax && m[lane] != 0);
-      const uint32_t b1 = __ballot_sync(ptx::FULL_MASK, 32 + lane <= Tmax && m[min(32 + lane, Tmax)] != 0);
-      const uint32_t b2 = __ballot_sync(ptx::FULL_MASK, lane == 0 && Tmax >= 64 && m[min(64, Tmax)] != 0);
+      const uint32_t b0 = __ballot_sync(ptx::FULL_MASK, (raw & 0xffu) != 0u);
+      const uint32_t b1 = __ballot_sync(ptx::FULL_MASK, (raw & 0xff00u) != 0u);
+      const uint32_t b2 = __ballot_sync(ptx::FULL_MASK, (raw & 0xff0000u) != 0u);
       const int end = b0 ? __ffs(b0) - 1 : b1 ? 32 + __ffs(b1) - 1 : b2 ? 64 : 1 + Tmax;
       len = end - 1;
     } else {
@@ -866,9 +890,18 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
     }
     return max(0, min(len, Tmax));
   };
-  // start the copies of this warp's frame block of one track
+  // start the copies of this warp's frame block of one track.  Frames past the block's end are read as ZEROS from the
+  // buffer (the dots and the weighted sums run unguarded, straight-line): whenever a block is shorter than the one
+  // the buffer held before, the stale frames in between are cleared first.
+  int nw_buf = FB;                     // frames of the buffer that may hold something else than zeros
   auto issue = [&](long long track, int len) {
     const int nw = max(0, min(len - FB * wg, FB));
+    if (nw < nw_buf) {                 // warp-uniform
+      float4* z = reinterpret_cast<float4*>(xs + (size_t)nw * D);
+      for (int i = lane; i < (nw_buf - nw) * (D / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ptx::fence_proxy_async_smem();   // these generic-proxy writes come before any later copy into the same bytes
+    }
+    nw_buf = nw;
     if (lane == 0) {
       if (nw > 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nw * (D * 4));
       else ptx::mbar_arrive(bar);
@@ -891,7 +924,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
   // the first track is requested before the CTA-wide set-up
   int len = 0;
   if (warp < GWARPS) {
-    len = track_len(first);
+    len = decode(first, peek(first));
     issue(first, len);
   }
   fused_setup<GW>(fz, warp, GWARPS);
@@ -919,12 +952,20 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
     load_m_tmem<GWARPS + HELPER_WARPS, 2>(p, meta, warp, lane);   // while the first frames are in flight
 #endif
     int it = 0;
+#ifdef SEAM_AGG_PHASES
+    long long ph_prev = clock64();
+    if (warp == 0 && lane < 16) s.phase[lane] = 0;
+    __syncwarp();
+#endif
 #pragma unroll 1
     for (long long track = first; track < p.Q; track += stride, ++it) {
+      SEAM_PH(0);
       ptx::mbar_wait(bar, (uint32_t)it & 1u, 106);
+      SEAM_PH(1);
       const int nw = max(0, min(len - FB * wg, FB));
 
-      // ---- my 16 frames -> registers, four dots per frame, totals of 4 frames per butterfly
+      // ---- my 16 frames -> registers (zeros past the block's end), four dots per frame, totals of 4 frames per butterfly
+      const uint32_t raw_next = peek(track + stride);
       Vec8 x[FB];
 #pragma unroll
       for (int t0 = 0; t0 < FB; t0 += 4) {
@@ -932,8 +973,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int t = t0 + u;
-          if (t < nw) x[t] = load_vec8(xs + t * D, lane);
-          else x[t] = zero_vec8();
+          x[t] = load_vec8(xs + t * D, lane);
           acc[4 * u + 0] = dot8(x[t], ut);
           acc[4 * u + 1] = dot8(x[t], wa);
           acc[4 * u + 2] = dot8(x[t], up);
@@ -943,16 +983,19 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
         // frame F = FB wg + t0 + (lane >> 2): a, d -> ad[F / 2][F % 2 (+ 2)], b, c -> bc[...], zero past the track's end
         if (lane < 16) sc_dst[2 * t0] = (comp < 2 || SF0 + t0 < len) ? tot + my_const : 0.f;
       }
+      SEAM_PH(2);
       // the buffer is free again: fetch this warp's block of the group's next track
-      const int len_next = track_len(track + stride);
+      const int len_next = decode(track + stride, raw_next);
       __syncwarp();
       issue(track + stride, len_next);
+      SEAM_PH(3);
 #if defined(SEAM_AGG_GDIAG) && SEAM_AGG_GDIAG == 1      // developer diagnostic (wrong results): frames -> registers + dots only
       if (len == -5) p.out[track] = x[3].a + x[15].d;
       len = len_next;
       continue;
 #endif
       ptx::named_bar_sync(bar_id, GW * 32);                       // #1 all scalars of the track are visible
+      SEAM_PH(4);
 
       // ---- attention over the track's frames: lane = (frame f of my block, half of the j / t range).  The loops
       // take two frames per step ({b_e, b_o, c_e, c_o}: one 16-byte load, one packed add, one packed fma) into two
@@ -999,7 +1042,9 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
         gs.red_max[wg] = m_w;
         gs.red_sum[wg] = z_w;
       }
+      SEAM_PH(5);
       ptx::named_bar_sync(bar_id, GW * 32);                       // #2 (also: nobody reads d any more)
+      SEAM_PH(6);
       float m = gs.red_max[0];
 #pragma unroll
       for (int w = 1; w < GW; ++w) m = fmaxf(m, gs.red_max[w]);
@@ -1011,10 +1056,11 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
       }
       const float p_t = valid ? expf(s_t - m) / z : 0.f;
       if (half == 0) gs.ad[F >> 1][2 + (F & 1)] = p_t;
-#if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3)
+#if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3) && !defined(SEAM_AGG_PHASES)
       if (p.att && half == 0 && F < Tmax) p.att[(size_t)track * Tmax + F] = p_t;
 #endif
       ptx::named_bar_sync(bar_id, GW * 32);                       // #4 all p_t are visible
+      SEAM_PH(7);
       float q_j = len > 1 ? interact(b_f, gs.ad) : 0.f;            // sum_t relu(b_j + a_t) p_t / T
       if (!valid) q_j = 0.f;
       const float qsum_w = ptx::warp_sum(half == 0 ? q_j : 0.f);
@@ -1026,6 +1072,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
       len = len_next;
       continue;
 #endif
+      SEAM_PH(8);
       // ---- partial weighted sums over my frames, 8 channels per lane.  {p, p}, {q, q} come from shared memory (one
       // broadcast load per frame, four in flight); frames past the block's end are zero in registers and need no guard.
       Vec8 pov = zero_vec8(), rv = zero_vec8();
@@ -1061,7 +1108,9 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
 #endif
         }
       }
+      SEAM_PH(9);
       ptx::named_bar_sync(bar_id, GW * 32);                       // #5 partial sums, maxima and the slot are visible
+      SEAM_PH(10);
 #ifdef SEAM_AGG_DIAG_NO_PUBLISH
       if (gs.red_rmax[0] == 123.456f) p.out[track] = gs.part[0][lane];
       len = len_next;
@@ -1080,6 +1129,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
         const float scale = track_scale(rb, &inv);
         if (warp == 0 && it == 40) SEAM_TL3(p, 6);
         ptx::mbar_wait(&meta->buf_free[buf], ((batch >> 1) & 1u) ^ 1u, 107);
+        SEAM_PH(11);
         if (warp == 0 && it == 40) SEAM_TL3(p, 7);
         uint8_t* rt = fz + OFF_RT + buf * RT_BYTES;
         constexpr int CW = D / GW;
@@ -1116,8 +1166,13 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&meta->tile_full[buf]);
       }
+      SEAM_PH(12);
       len = len_next;
     }
+#ifdef SEAM_AGG_PHASES
+    __syncwarp();
+    if (warp == 0 && lane < 16 && p.att) reinterpret_cast<long long*>(p.att)[blockIdx.x * 16 + lane] = lane == 15 ? (long long)it : s.phase[lane];
+#endif
   }
   fused_teardown(fz, warp, GWARPS);
   if (p.x_on && p.x_last) xchg::signal_all(p.x, xchg::KIND_Q, xstep);

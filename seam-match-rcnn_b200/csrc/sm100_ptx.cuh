@@ -380,10 +380,11 @@ __device__ __forceinline__ float warp_sum_b(float v) {
   v += __shfl_xor_sync(FULL_MASK, v, 16);
   return v;
 }
+// one CREDUX.MAX.F32 (sm_100a) instead of five shuffle + max rounds; all 32 lanes must call it converged
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 // Transposing butterfly: N per-lane values (N = 8, 16, 32) are summed over the 32 lanes; lane l
