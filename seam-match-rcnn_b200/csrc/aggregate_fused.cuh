@@ -998,70 +998,80 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
       SEAM_PH(4);
 
       // ---- attention over the track's frames: lane = (frame f of my block, half of the j / t range).  The loops
-      // take two frames per step ({b_e, b_o, c_e, c_o}: one 16-byte load, one packed add, one packed fma) into two
-      // independent accumulators; the 1/T factor is applied once at the end.
+      // take two frames per step ({b_e, b_o, c_e, c_o}: one 16-byte load, one packed add, one packed fma) and run over
+      // ALL FB GW frames without bounds (straight-line code): past the track's end c, and later e, are zero.  The 1/T
+      // factor is applied once at the end.
       const int f = lane & 15, half = lane >> 4;
       const int F = FB * wg + f;
       const bool valid = F < len;
-      const int npairs = (len + 1) >> 1;
       const float inv_len = len > 0 ? 1.f / (float)len : 0.f;
       const float a_f = gs.ad[F >> 1][F & 1], d_f = gs.ad[F >> 1][2 + (F & 1)], b_f = gs.bc[F >> 1][F & 1];
-      auto interact = [&](const float own, const float (*tab)[4]) -> float {   // sum_j relu(own + tab.x_j) * tab.y_j
-        const u64 o2 = pk(own, own);
+      // sum over the 8 pairs of block w this lane's half takes: relu(own + tab.x) * tab.y
+      auto block_sum = [&](const u64 o2, const float (*tab)[4], int w) -> float {
         u64 acc_a = 0ull, acc_b = 0ull;
-        int jj = half;
-        for (; jj + 2 < npairs; jj += 4) {
-          const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(&tab[jj][0]);
-          const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(&tab[jj + 2][0]);
+#pragma unroll
+        for (int i = 0; i < FB / 2; i += 4) {
+          const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(&tab[(FB / 2) * w + i + half][0]);
+          const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(&tab[(FB / 2) * w + i + 2 + half][0]);
           float s0, s1, s2, s3;
           upk(add2(o2, v0.x), s0, s1);
           upk(add2(o2, v1.x), s2, s3);
           acc_a = fma2(pk(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), v0.y, acc_a);
           acc_b = fma2(pk(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), v1.y, acc_b);
         }
-        if (jj < npairs) {
-          const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(&tab[jj][0]);
-          float s0, s1;
-          upk(add2(o2, v0.x), s0, s1);
-          acc_a = fma2(pk(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), v0.y, acc_a);
-        }
         float lo, hi, lo2, hi2;
         upk(acc_a, lo, hi);
         upk(acc_b, lo2, hi2);
-        float r = (lo + hi) + (lo2 + hi2);
-        r += __shfl_xor_sync(ptx::FULL_MASK, r, 16);
-        return r * inv_len;
+        return (lo + hi) + (lo2 + hi2);
       };
-      const float sum = len > 1 ? interact(a_f, gs.bc) : 0.f;
+      float sum = 0.f;
+      if (len > 1) {
+        const u64 a2 = pk(a_f, a_f);
+#pragma unroll
+        for (int w = 0; w < GW; ++w) sum += block_sum(a2, gs.bc, w);
+        sum += __shfl_xor_sync(ptx::FULL_MASK, sum, 16);
+        sum *= inv_len;
+      }
       const float s_t = valid ? d_f + sum + c_s : -INFINITY;
-      // softmax over the track with ONE barrier: every warp publishes the maximum of its block and the sum of
-      // exp(s - its maximum); m = max_w m_w, z = sum_w z_w exp(m_w - m), p_t = exp(s_t - m) / z
+      // Softmax over the track with ONE barrier and no second pass over p: every warp publishes the maximum m_w of its
+      // block, e_t = exp(s_t - m_w) for its frames and z_w = sum e_t.  After the barrier m = max_w m_w,
+      // z = sum_w z_w exp(m_w - m), p_t = e_t exp(m_w - m) / z, and the second interaction sums e_t block by block,
+      // scaling each block's sum by exp(m_w - m).
       const float m_w = ptx::warp_max(s_t);
-      const float z_w = ptx::warp_sum(half == 0 && valid ? expf(s_t - m_w) : 0.f);
+      const float e_t = valid ? expf(s_t - m_w) : 0.f;
+      const float z_w = ptx::warp_sum(half == 0 ? e_t : 0.f);
+      if (half == 0) gs.ad[F >> 1][2 + (F & 1)] = e_t;            // d (read above by both lanes of the frame) -> e
       if (lane == 0) {
         gs.red_max[wg] = m_w;
         gs.red_sum[wg] = z_w;
       }
       SEAM_PH(5);
-      ptx::named_bar_sync(bar_id, GW * 32);                       // #2 (also: nobody reads d any more)
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #2 e, m_w, z_w of the whole track are visible
       SEAM_PH(6);
       float m = gs.red_max[0];
 #pragma unroll
       for (int w = 1; w < GW; ++w) m = fmaxf(m, gs.red_max[w]);
-      float z = 0.f;
+      float scale[GW], z = 0.f;
 #pragma unroll
       for (int w = 0; w < GW; ++w) {
         const float mw = gs.red_max[w];
-        if (mw > -INFINITY) z += gs.red_sum[w] * expf(mw - m);     // a warp without frames of this track: (-inf, 0)
+        scale[w] = mw > -INFINITY ? expf(mw - m) : 0.f;            // a warp without frames of this track: (-inf, 0)
+        z = fmaf(gs.red_sum[w], scale[w], z);
       }
-      const float p_t = valid ? expf(s_t - m) / z : 0.f;
-      if (half == 0) gs.ad[F >> 1][2 + (F & 1)] = p_t;
+      const float inv_z = z > 0.f ? 1.f / z : 0.f;
+      const float p_t = e_t * scale[wg] * inv_z;
 #if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3) && !defined(SEAM_AGG_PHASES)
       if (p.att && half == 0 && F < Tmax) p.att[(size_t)track * Tmax + F] = p_t;
 #endif
-      ptx::named_bar_sync(bar_id, GW * 32);                       // #4 all p_t are visible
       SEAM_PH(7);
-      float q_j = len > 1 ? interact(b_f, gs.ad) : 0.f;            // sum_t relu(b_j + a_t) p_t / T
+      float q_j = 0.f;                                             // sum_t relu(b_j + a_t) p_t / T
+      if (len > 1) {
+        const u64 b2 = pk(b_f, b_f);
+#pragma unroll
+        for (int w = 0; w < GW; ++w) q_j = fmaf(block_sum(b2, gs.ad, w), scale[w], q_j);
+        q_j += __shfl_xor_sync(ptx::FULL_MASK, q_j, 16);
+        q_j *= inv_len * inv_z;
+      }
       if (!valid) q_j = 0.f;
       const float qsum_w = ptx::warp_sum(half == 0 ? q_j : 0.f);
       if (half == 0) *reinterpret_cast<float4*>(&gs.pq[F][0]) = make_float4(p_t, p_t, q_j, q_j);
