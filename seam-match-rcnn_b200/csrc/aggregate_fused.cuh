@@ -996,6 +996,11 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
 #endif
       ptx::named_bar_sync(bar_id, GW * 32);                       // #1 all scalars of the track are visible
       SEAM_PH(4);
+#ifndef SEAM_AGG_DIAG_NO_PUBLISH
+      // the track's slot in the batch under construction is claimed now, its (~200 cycle) round trip used much later
+      unsigned my_slot = 0u;
+      if (wg == 0 && lane == 0) my_slot = atomicAdd(&meta->next_slot, 1u);
+#endif
 
       // ---- attention over the track's frames: lane = (frame f of my block, half of the j / t range).  The loops
       // take two frames per step ({b_e, b_o, c_e, c_o}: one 16-byte load, one packed add, one packed fma) and run over
@@ -1006,8 +1011,8 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
       const bool valid = F < len;
       const float inv_len = len > 0 ? 1.f / (float)len : 0.f;
       const float a_f = gs.ad[F >> 1][F & 1], d_f = gs.ad[F >> 1][2 + (F & 1)], b_f = gs.bc[F >> 1][F & 1];
-      // sum over the 8 pairs of block w this lane's half takes: relu(own + tab.x) * tab.y
-      auto block_sum = [&](const u64 o2, const float (*tab)[4], int w) -> float {
+      // sum over the 8 pairs of block w this lane's half takes: relu(own + tab.x) * tab.y; *ysum += sum of tab.y
+      auto block_sum = [&](const u64 o2, const float (*tab)[4], int w, u64* ysum) -> float {
         u64 acc_a = 0ull, acc_b = 0ull;
 #pragma unroll
         for (int i = 0; i < FB / 2; i += 4) {
@@ -1018,6 +1023,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
           upk(add2(o2, v1.x), s2, s3);
           acc_a = fma2(pk(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), v0.y, acc_a);
           acc_b = fma2(pk(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), v1.y, acc_b);
+          if (ysum) *ysum = add2(*ysum, add2(v0.y, v1.y));
         }
         float lo, hi, lo2, hi2;
         upk(acc_a, lo, hi);
@@ -1028,50 +1034,52 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
       if (len > 1) {
         const u64 a2 = pk(a_f, a_f);
 #pragma unroll
-        for (int w = 0; w < GW; ++w) sum += block_sum(a2, gs.bc, w);
+        for (int w = 0; w < GW; ++w) sum += block_sum(a2, gs.bc, w, nullptr);
         sum += __shfl_xor_sync(ptx::FULL_MASK, sum, 16);
         sum *= inv_len;
       }
       const float s_t = valid ? d_f + sum + c_s : -INFINITY;
       // Softmax over the track with ONE barrier and no second pass over p: every warp publishes the maximum m_w of its
-      // block, e_t = exp(s_t - m_w) for its frames and z_w = sum e_t.  After the barrier m = max_w m_w,
-      // z = sum_w z_w exp(m_w - m), p_t = e_t exp(m_w - m) / z, and the second interaction sums e_t block by block,
-      // scaling each block's sum by exp(m_w - m).
+      // block and e_t = exp(s_t - m_w) for its frames.  After the barrier m = max_w m_w; the second interaction sums
+      // e_t block by block -- and the e_t themselves on the way: z = sum_w exp(m_w - m) sum_{t in w} e_t, no reduction
+      // of its own -- scaling each block's sums by exp(m_w - m); p_t = e_t exp(m_w - m) / z.
       const float m_w = ptx::warp_max(s_t);
       const float e_t = valid ? expf(s_t - m_w) : 0.f;
-      const float z_w = ptx::warp_sum(half == 0 ? e_t : 0.f);
       if (half == 0) gs.ad[F >> 1][2 + (F & 1)] = e_t;            // d (read above by both lanes of the frame) -> e
-      if (lane == 0) {
-        gs.red_max[wg] = m_w;
-        gs.red_sum[wg] = z_w;
-      }
+      if (lane == 0) gs.red_max[wg] = m_w;
       SEAM_PH(5);
-      ptx::named_bar_sync(bar_id, GW * 32);                       // #2 e, m_w, z_w of the whole track are visible
+      ptx::named_bar_sync(bar_id, GW * 32);                       // #2 e and m_w of the whole track are visible
       SEAM_PH(6);
       float m = gs.red_max[0];
 #pragma unroll
       for (int w = 1; w < GW; ++w) m = fmaxf(m, gs.red_max[w]);
-      float scale[GW], z = 0.f;
+      float scale[GW];
 #pragma unroll
       for (int w = 0; w < GW; ++w) {
         const float mw = gs.red_max[w];
-        scale[w] = mw > -INFINITY ? expf(mw - m) : 0.f;            // a warp without frames of this track: (-inf, 0)
-        z = fmaf(gs.red_sum[w], scale[w], z);
+        scale[w] = mw > -INFINITY ? expf(mw - m) : 0.f;            // a warp without frames of this track: -inf
+      }
+      SEAM_PH(7);
+      float q_j = 0.f, z = 0.f;                                    // q_j = sum_t relu(b_j + a_t) p_t / T
+      {
+        const u64 b2 = pk(b_f, b_f);
+#pragma unroll
+        for (int w = 0; w < GW; ++w) {
+          u64 ys = 0ull;
+          q_j = fmaf(block_sum(b2, gs.ad, w, &ys), scale[w], q_j);
+          float y0, y1;
+          upk(ys, y0, y1);
+          z = fmaf(y0 + y1, scale[w], z);
+        }
+        q_j += __shfl_xor_sync(ptx::FULL_MASK, q_j, 16);
+        z += __shfl_xor_sync(ptx::FULL_MASK, z, 16);
       }
       const float inv_z = z > 0.f ? 1.f / z : 0.f;
       const float p_t = e_t * scale[wg] * inv_z;
+      q_j = len > 1 ? q_j * inv_len * inv_z : 0.f;
 #if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3) && !defined(SEAM_AGG_PHASES)
       if (p.att && half == 0 && F < Tmax) p.att[(size_t)track * Tmax + F] = p_t;
 #endif
-      SEAM_PH(7);
-      float q_j = 0.f;                                             // sum_t relu(b_j + a_t) p_t / T
-      if (len > 1) {
-        const u64 b2 = pk(b_f, b_f);
-#pragma unroll
-        for (int w = 0; w < GW; ++w) q_j = fmaf(block_sum(b2, gs.ad, w), scale[w], q_j);
-        q_j += __shfl_xor_sync(ptx::FULL_MASK, q_j, 16);
-        q_j *= inv_len * inv_z;
-      }
       if (!valid) q_j = 0.f;
       const float qsum_w = ptx::warp_sum(half == 0 ? q_j : 0.f);
       if (half == 0) *reinterpret_cast<float4*>(&gs.pq[F][0]) = make_float4(p_t, p_t, q_j, q_j);
@@ -1114,7 +1122,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
           gs.red_q[wg] = qsum_w;
           gs.red_rmax[wg] = pm;
 #ifndef SEAM_AGG_DIAG_NO_PUBLISH
-          if (wg == 0) gs.slot = atomicAdd(&meta->next_slot, 1u);
+          if (wg == 0) gs.slot = my_slot;
 #endif
         }
       }
