@@ -197,10 +197,7 @@ __device__ __forceinline__ float track_scale(float mx, float* inv) {
 struct Slot {
   int buf, pos;
 };
-__device__ __forceinline__ Slot claim_slot(Meta* meta, int lane) {
-  unsigned s = 0;
-  if (lane == 0) s = atomicAdd(&meta->next_slot, 1u);
-  s = __shfl_sync(ptx::FULL_MASK, s, 0);
+__device__ __forceinline__ Slot wait_slot(Meta* meta, unsigned s) {   // s = the track's ticket (atomicAdd on next_slot)
   const unsigned batch = s / NB;
   Slot sl;
   sl.buf = (int)(batch & 1u);
@@ -648,6 +645,12 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         constexpr bool FULL = decltype(full_tag)::value;
         // ---- frames -> registers, four dots per frame; every 4 frames a transposing butterfly leaves
         // the 16 totals (a, d, b, c of 4 frames) in lanes 0..15
+#ifndef SEAM_AGG_DIAG_NO_PUBLISH
+        // the track's slot in the batch under construction: the shared-memory atomic's round trip (~200 cycles) is
+        // started here and used after the weighted sums
+        unsigned ticket = 0u;
+        if (lane == 0) ticket = atomicAdd(&meta->next_slot, 1u);
+#endif
         Vec8 x[TR];
 #pragma unroll
         for (int t0 = 0; t0 < TR; t0 += 4) {
@@ -688,11 +691,12 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         // ---- attention over the track's frames (lane = frame)
         const int L = FULL ? TR : len;
         const bool valid = lane < L;
+        const bool many = FULL ? TR > 1 : len > 1;
         const float inv_len = FULL ? 1.f / (float)TR : (len > 0 ? 1.f / (float)len : 0.f);
         float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) sc = *reinterpret_cast<const float4*>(scal + 4 * lane);   // a, d, b, c of my frame
         float sum = 0.f;
-        if (FULL ? TR > 1 : len > 1) {
+        if (many) {
 #pragma unroll
           for (int j = 0; j < (FULL ? TR : len); ++j) {
             const float2 bc = *reinterpret_cast<const float2*>(scal + 4 * j + 2);
@@ -702,44 +706,44 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         const float s_t = valid ? sc.y + sum + c_s : -INFINITY;
         const float m = ptx::warp_max(s_t);
         const float e_t = valid ? expf(s_t - m) : 0.f;
-        const float z = ptx::warp_sum(e_t);
-        const float p_t = valid ? e_t / z : 0.f;
         __syncwarp();                                    // all lanes have read b, c, d
-        if (lane < TR) {
-          scal[4 * lane + 1] = p_t;
-          scal[4 * lane + 2] = p_t;
-        }
+        if (lane < TR) scal[4 * lane + 1] = e_t;         // d -> e
         __syncwarp();
-        float q_j = 0.f;
-        if ((FULL ? TR > 1 : len > 1) && valid) {
+        // One loop gives the softmax denominator (every lane sums the e_t itself: no reduction) and the second
+        // interaction q_j = sum_t p_t relu(a_t + b_j) / T, p_t = e_t / z.
+        float z = 0.f, q_j = 0.f;
 #pragma unroll
-          for (int t = 0; t < (FULL ? TR : len); ++t) {
-            const float2 ap = *reinterpret_cast<const float2*>(scal + 4 * t);
-            q_j = fmaf(ap.y, fmaxf(ap.x + sc.z, 0.f) * inv_len, q_j);
-          }
+        for (int t = 0; t < (FULL ? TR : len); ++t) {
+          const float2 ae = *reinterpret_cast<const float2*>(scal + 4 * t);
+          z += ae.y;
+          q_j = fmaf(ae.y, fmaxf(ae.x + sc.z, 0.f), q_j);
         }
-        const float qsum = ptx::warp_sum(q_j);
-        __syncwarp();                                    // all lanes have read the a_t
+        const float inv_z = z > 0.f ? 1.f / z : 0.f;
+        const float p_t = e_t * inv_z;
+        q_j = (many && valid) ? q_j * inv_len * inv_z : 0.f;
+        __syncwarp();                                    // all lanes have read the a_t, e_t
         if (lane < TR) *reinterpret_cast<float4*>(scal + 4 * lane) = make_float4(p_t, p_t, q_j, q_j);
 #if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3)
         if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
 #endif
         __syncwarp();
 
-        // ---- weighted sums over frames, 8 channels per lane
+        // ---- weighted sums over frames, 8 channels per lane; sum_j q_j on the way (every lane adds the broadcast q)
         Vec8 pov = zero_vec8(), rv = zero_vec8();
+        float qsum = 0.f;
 #pragma unroll
         for (int t = 0; t < TR; ++t) {
           if (FULL || t < len) {
             const ulonglong2 pq = *reinterpret_cast<const ulonglong2*>(scal + 4 * t);   // {p,p}, {q,q}
             fma8(pov, pq.x, x[t]);
             fma8(rv, pq.y, x[t]);
+            qsum += __uint_as_float((uint32_t)(pq.y & 0xffffffffull));
           }
         }
         float4 po0, po1, r0, r1;
         unpack_vec8(pov, po0, po1);
         unpack_vec8(rv, r0, r1);
-        if (FULL ? TR > 1 : len > 1) {
+        if (many) {
           const float4 wbg0 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 4 * lane);
           const float4 wbg1 = *reinterpret_cast<const float4*>(fold + Fold::WBG + 128 + 4 * lane);
           const float4 bw0 = *reinterpret_cast<const float4*>(fold + Fold::BW + 4 * lane);
@@ -764,7 +768,7 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         return;
 #endif
         if (warp == 0 && it == 5) SEAM_TL3(p, 6);
-        const Slot sl = claim_slot(meta, lane);
+        const Slot sl = wait_slot(meta, __shfl_sync(ptx::FULL_MASK, ticket, 0));
         if (warp == 0 && it == 5) SEAM_TL3(p, 7);
         uint8_t* rt = fz + OFF_RT + sl.buf * RT_BYTES;
         store_r4(rt, sl.pos, 4 * lane, r0, s);

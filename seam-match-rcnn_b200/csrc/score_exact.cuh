@@ -277,6 +277,7 @@ __device__ __forceinline__ void rescore_merge32(const uint2* wb, int begin, int 
   wsort::merge32<true>(cv, cidx, lane);
 }
 
+// (launch bounds of 5 CTAs per SM = 48 registers were measured: 168 bytes of spills, 70 -> 83 us)
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   __shared__ uint2 wbuf[8][RESCORE_WBUF];
   __shared__ uint4 qbuf[8][64];
