@@ -13,9 +13,13 @@ for _ in range(3):
 torch.cuda.synchronize()
 ph = att.view(-1)[:148 * 32].view(torch.int64).view(148, 16).cpu().double()
 its = ph[:, 15].clamp(min=1)
+names_w = ["loop top", "wait for the frames", "frames -> registers, dots, butterflies", "issue the next track's copy, peek", "interaction 1, max, e",
+           "interaction 2 + z, {p,q} store", "weighted sums, |r| max", "wait for the batch slot", "publish (r split, pooled, fence, arrive)"]
 names = ["loop top", "wait for the frames", "frames -> registers, dots, butterflies", "issue the next block's copy", "barrier 1 (scalars)",
          "interaction pass 1 + local softmax", "barrier 2", "p_t, barrier 4", "interaction pass 2, q sum, {p,q} store",
          "weighted sums, partials, |r| max", "barrier 5", "finishing: wait for the batch buffer", "finishing: sums, store, publish"]
+if T <= 16:
+    names = names_w
 tot = 0.0
 for i, n in enumerate(names):
     c = (ph[:, i] / its)

@@ -117,6 +117,13 @@ using ptx::treduce;
 #define SEAM_PH(i) do { } while (0)
 #endif
 
+// the same for the short-track kernel at TR = 10 (the counters live in the unused tail of warp 0's scalar block)
+#ifdef SEAM_AGG_PHASES
+#define SEAM_WPH(i) do { if (TR == 10 && warp == 0 && lane == 0) { const long long t_ = clock64(); reinterpret_cast<long long*>(scal + 40)[i] += t_ - ph_prev; ph_prev = t_; } } while (0)
+#else
+#define SEAM_WPH(i) do { } while (0)
+#endif
+
 // ---- packed fp32 pairs (FFMA2 / FMUL2): the streaming pass is bound by instruction issue
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) {
@@ -449,7 +456,7 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
 
 // one-time CTA set-up shared by both kernels: barriers, slot counter, tensor-memory allocation
 template <int ARRIVALS>
-__device__ __forceinline__ void fused_setup(uint8_t* fz, int warp, int helper0) {
+__device__ __forceinline__ void fused_setup(uint8_t* fz, int warp, int helper0, int m_warps) {
   Meta* meta = reinterpret_cast<Meta*>(fz + OFF_META);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -457,7 +464,7 @@ __device__ __forceinline__ void fused_setup(uint8_t* fz, int warp, int helper0) 
       ptx::mbar_init(&meta->buf_free[i], HELPER_WARPS);
     }
     ptx::mbar_init(&meta->acc_full, 1);
-    ptx::mbar_init(&meta->m_ready, SEAM_AGG_INIT_WARPS(blockDim.x >> 5));
+    ptx::mbar_init(&meta->m_ready, SEAM_AGG_INIT_WARPS(m_warps));
     meta->next_slot = 0u;
     ptx::fence_mbar_init();
   }
@@ -485,12 +492,17 @@ __global__ void signal_only_kernel(const xchg::Exchange x) {
 // ================================================================================================
 template <int TR>
 struct Cfg;
+// LOADER (TR = 10): the sixteenth warp issues the copies of every producer's next track instead of a twelfth producer.
+// Handing a box to the copy engine costs the issuing warp 400-900 cycles (it queues behind the other warps' boxes;
+// 1,400-1,500 cycles as per-frame copies) -- 15 % of a producer's iteration when the producers issue their own.
+// A seventeenth warp is not an option: the register file is four files of 16 K, one per scheduler, a fifth warp on one
+// of them caps the launch count at 96 registers and the producers at 128 (they hold 80 of frames + 32 of weights).
 template <>
-struct Cfg<4> { static constexpr int NW = 16, SLOTS = 2, REGS_P = 104, REGS_H = 56; };   // the pool holds what the helpers release
+struct Cfg<4> { static constexpr int NW = 16, SLOTS = 2, LOADER = 0, REGS_P = 104, REGS_H = 56; };   // the pool holds what the helpers release
 template <>
-struct Cfg<10> { static constexpr int NW = 12, SLOTS = 1, REGS_P = 152, REGS_H = 56; };
+struct Cfg<10> { static constexpr int NW = 11, SLOTS = 1, LOADER = 1, REGS_P = 152, REGS_H = 56; };
 template <>
-struct Cfg<16> { static constexpr int NW = 8, SLOTS = 1, REGS_P = 224, REGS_H = 56; };
+struct Cfg<16> { static constexpr int NW = 8, SLOTS = 1, LOADER = 0, REGS_P = 224, REGS_H = 56; };
 
 #ifndef SEAM_AGG_M_INFLIGHT
 #define SEAM_AGG_M_INFLIGHT 4
@@ -500,15 +512,18 @@ constexpr size_t warp_smem_bytes() {
   return 1024 + fused_bytes<true>() + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * TR * D * 4   // track buffers
          + (size_t)Cfg<TR>::NW * 64 * 4                                                   // per-warp scalars
          + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * 8                                       // mbarriers
+         + (size_t)Cfg<TR>::NW * 8                                                        // "buffer is free" mbarriers
          + (size_t)Cfg<TR>::NW * Cfg<TR>::SLOTS * 4;                                      // track lengths
 }
 template <int TR>
-constexpr int warp_threads() { return (Cfg<TR>::NW + HELPER_WARPS) * 32; }
+constexpr int warp_threads() { return (Cfg<TR>::NW + HELPER_WARPS + Cfg<TR>::LOADER) * 32; }
 
 template <int TR>
-__global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS) * 32, 1)
+__global__ void __launch_bounds__((Cfg<TR>::NW + HELPER_WARPS + Cfg<TR>::LOADER) * 32, 1)
 aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Params p) {
   constexpr int NW = Cfg<TR>::NW, SLOTS = Cfg<TR>::SLOTS;
+  constexpr bool LOADER = Cfg<TR>::LOADER != 0;
+  static_assert(!LOADER || SLOTS == 1, "the loader warp serves single-buffer producers");
   constexpr int M_INFLIGHT = TR >= 10 ? SEAM_AGG_M_INFLIGHT : 2;     // chunks of M a producer warp has in flight at start
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -528,9 +543,15 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
   uint64_t* bars = reinterpret_cast<uint64_t*>(pz + (size_t)NW * SLOTS * TR * D * 4 + (size_t)NW * 64 * 4) +
                    (warp < NW ? warp : 0) * SLOTS;
   int* slot_len = reinterpret_cast<int*>(pz + (size_t)NW * SLOTS * TR * D * 4 + (size_t)NW * 64 * 4 +
-                                         (size_t)NW * SLOTS * 8) + (warp < NW ? warp : 0) * SLOTS;
+                                         (size_t)NW * SLOTS * 8 + (size_t)NW * 8) + (warp < NW ? warp : 0) * SLOTS;
+  // loader's view: every producer's buffer, barriers and track length
+  float* const xbuf_all = reinterpret_cast<float*>(pz);
+  uint64_t* const bars_all = reinterpret_cast<uint64_t*>(pz + (size_t)NW * SLOTS * TR * D * 4 + (size_t)NW * 64 * 4);
+  uint64_t* const empty_all = bars_all + NW * SLOTS;                                    // producer -> loader: frames are in registers
+  int* const slot_len_all = reinterpret_cast<int*>(empty_all + NW);
   if (warp < NW && lane == 0) {
     for (int i = 0; i < SLOTS; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::mbar_init(&empty_all[warp], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 0) SEAM_TL(p, 0);
@@ -593,19 +614,72 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
     for (int i = 0; i < AHEAD; ++i) issue(first + i * stride, i, peek(first + i * stride));
     raw_next = peek(first + (long long)AHEAD * stride);
   }
-  fused_setup<1>(fz, warp, NW);
+  fused_setup<1>(fz, warp, NW, NW + HELPER_WARPS + Cfg<TR>::LOADER);
   if (warp == 0) SEAM_TL2(p, 1);
 
-  if (warp >= NW) {
+  if (LOADER && warp == NW + HELPER_WARPS) {
+    // ------------------------------------------------------------------------------ loader warp: lane w serves producer w
+    load_m_tmem<NW + HELPER_WARPS + 1, 2>(p, meta, warp, lane);   // its share of M first: sixteen warps fill tensor memory
+    auto lane_len = [&](long long track) -> int {       // one lane scans the mask row (independent byte loads)
+      int len;
+      if (p.lens) {
+        len = p.lens[track];
+      } else if (p.mask) {
+        const uint8_t* m = p.mask + (size_t)track * (1 + Tmax);
+        int end = 1 + Tmax;
+        for (int i = Tmax; i >= 0; --i)
+          if (m[i] != 0) end = i;                       // first nonzero ends the track (models/match_head.py:136-139)
+        len = end - 1;
+      } else {
+        len = Tmax;
+      }
+      return max(0, min(len, Tmax));
+    };
+    long long next = first0 + lane + stride;            // the producer's second track (it requested the first itself)
+    uint32_t ph = 0u;
+    bool active = lane < NW && next < p.Q;
+    int len_next = active ? lane_len(next) : 0;
+    uint64_t t0 = 0;
+    while (__any_sync(ptx::FULL_MASK, active)) {
+      const bool ready = active && ptx::mbar_test_wait(&empty_all[lane < NW ? lane : 0], ph);
+      if (ready) {
+        uint64_t* bar = &bars_all[lane];
+        float* dst = xbuf_all + (size_t)lane * TR * D;
+        slot_len_all[lane] = len_next;
+        if (len_next > 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)len_next * (D * 4));
+        else ptx::mbar_arrive(bar);
+        if (TR >= 10 && p.use_tm && len_next == TR) {
+          ptx::tma_load_3d_hint(dst, &tmSeq, bar, 0, (int)next, 1, pol);
+        } else {
+          for (int t = 0; t < len_next; ++t)
+            ptx::bulk_load_1d_hint(dst + (size_t)t * D, p.seq + (long long)(t + 1) * p.frame_stride + next * p.track_stride,
+                                   D * 4, bar, pol);
+        }
+        next += stride;
+        ph ^= 1u;
+        active = next < p.Q;
+        len_next = active ? lane_len(next) : 0;
+      }
+      if (!__any_sync(ptx::FULL_MASK, ready)) {
+        __nanosleep(100);
+        const uint64_t now = ptx::globaltimer_ns();     // watchdog: a protocol error traps instead of hanging
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) ptx::watchdog_trap(109u, ptx::smem_u32(&empty_all[lane < NW ? lane : 0]), ph);
+      } else {
+        t0 = 0;
+      }
+    }
+  } else if (warp >= NW) {
     ptx::reg_dec<Cfg<TR>::REGS_H>();
-    load_m_tmem<SEAM_AGG_INIT_WARPS(NW + HELPER_WARPS), 2>(p, meta, SEAM_AGG_INIT_WARPS(NW + HELPER_WARPS) == HELPER_WARPS ? warp - NW : warp, lane);
-    helper_role<1, true>(p, fz, warp - NW, lane, NW, first0, stride, out_local, xstep);
+    // a warp reaches the tensor-memory lanes of ITS quarter (warp % 4): that is the helper's index
+    load_m_tmem<NW + HELPER_WARPS + Cfg<TR>::LOADER, 2>(p, meta, warp, lane);
+    helper_role<1, true>(p, fz, warp & 3, lane, NW, first0, stride, out_local, xstep);
   } else {
     ptx::reg_inc<Cfg<TR>::REGS_P>();
     if (warp == 0) SEAM_TL2(p, 2);
     if (warp == 0) SEAM_TL2(p, 3);
 #ifndef SEAM_AGG_HELPER_INIT
-    load_m_tmem<NW + HELPER_WARPS, M_INFLIGHT>(p, meta, warp, lane);   // while the first frames are in flight
+    load_m_tmem<NW + HELPER_WARPS + Cfg<TR>::LOADER, M_INFLIGHT>(p, meta, warp, lane);   // while the first frames are in flight
     if (warp == 0) SEAM_TL(p, 1);
     if (warp == 0) SEAM_TL2(p, 4);
 #endif
@@ -622,8 +696,14 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
                          : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
 
     int it = 0;
+#ifdef SEAM_AGG_PHASES
+    long long ph_prev = clock64();
+    if (TR == 10 && warp == 0 && lane < 24) scal[40 + lane] = 0.f;
+    __syncwarp();
+#endif
 #pragma unroll 1
     for (long long track = first; track < p.Q; track += stride, ++it) {
+      SEAM_WPH(0);
       const int slot = it % SLOTS;
       const uint32_t phase = (uint32_t)(it / SLOTS) & 1u;
       if constexpr (SLOTS > 1) {
@@ -632,6 +712,7 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         raw_next = peek(track + (long long)SLOTS * stride);
       }
       ptx::mbar_wait(&bars[slot], phase, 105);
+      SEAM_WPH(1);
       if (warp == 0 && it == 0) SEAM_TL(p, 2);
       if (warp == 0 && it == 0) SEAM_TL2(p, 5);
       if (warp == 0 && it == 1) SEAM_TL2(p, 6);
@@ -681,12 +762,13 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
             if (lane < 4 * nf) scal[4 * t0 + lane] = tot + my_const;
           }
         }
+        SEAM_WPH(2);
         if constexpr (SLOTS == 1) {
-          __syncwarp();                                // all lanes hold their frames in registers
-          issue(track + stride, 0, raw_next);
-          raw_next = peek(track + 2 * stride);
+          __syncwarp();                                // all lanes hold their frames in registers:
+          if (lane == 0) ptx::mbar_arrive(&empty_all[warp]);   // the loader warp may refill the buffer
         }
         __syncwarp();
+        SEAM_WPH(3);
 
         // ---- attention over the track's frames (lane = frame)
         const int L = FULL ? TR : len;
@@ -709,6 +791,7 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         __syncwarp();                                    // all lanes have read b, c, d
         if (lane < TR) scal[4 * lane + 1] = e_t;         // d -> e
         __syncwarp();
+        SEAM_WPH(4);
         // One loop gives the softmax denominator (every lane sums the e_t itself: no reduction) and the second
         // interaction q_j = sum_t p_t relu(a_t + b_j) / T, p_t = e_t / z.
         float z = 0.f, q_j = 0.f;
@@ -723,11 +806,12 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         q_j = (many && valid) ? q_j * inv_len * inv_z : 0.f;
         __syncwarp();                                    // all lanes have read the a_t, e_t
         if (lane < TR) *reinterpret_cast<float4*>(scal + 4 * lane) = make_float4(p_t, p_t, q_j, q_j);
-#if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3)
+#if !defined(SEAM_AGG_TIMELINE) && !defined(SEAM_AGG_TIMELINE2) && !defined(SEAM_AGG_TIMELINE3) && !defined(SEAM_AGG_PHASES)
         if (p.att && lane < Tmax) p.att[(size_t)track * Tmax + lane] = p_t;
 #endif
         __syncwarp();
 
+        SEAM_WPH(5);
         // ---- weighted sums over frames, 8 channels per lane; sum_j q_j on the way (every lane adds the broadcast q)
         Vec8 pov = zero_vec8(), rv = zero_vec8();
         float qsum = 0.f;
@@ -767,8 +851,10 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         if (mx == 123.456f) p.out[track] = s + po0.x + po1.y + r0.x + r1.w;
         return;
 #endif
+        SEAM_WPH(6);
         if (warp == 0 && it == 5) SEAM_TL3(p, 6);
         const Slot sl = wait_slot(meta, __shfl_sync(ptx::FULL_MASK, ticket, 0));
+        SEAM_WPH(7);
         if (warp == 0 && it == 5) SEAM_TL3(p, 7);
         uint8_t* rt = fz + OFF_RT + sl.buf * RT_BYTES;
         store_r4(rt, sl.pos, 4 * lane, r0, s);
@@ -783,10 +869,16 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         ptx::fence_proxy_async_smem();                   // the r rows are read by the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&meta->tile_full[sl.buf]);
+        SEAM_WPH(8);
       };
       if (len == TR) process(std::true_type{});
       else process(std::false_type{});
     }
+#ifdef SEAM_AGG_PHASES
+    __syncwarp();
+    if (TR == 10 && warp == 0 && lane < 16 && p.att)
+      reinterpret_cast<long long*>(p.att)[blockIdx.x * 16 + lane] = lane == 15 ? (long long)it : lane < 12 ? reinterpret_cast<long long*>(scal + 40)[lane] : 0ll;
+#endif
   }
   fused_teardown(fz, warp, NW);
   if (p.x_on && p.x_last) xchg::signal_all(p.x, xchg::KIND_Q, xstep);
@@ -931,7 +1023,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
     len = decode(first, peek(first));
     issue(first, len);
   }
-  fused_setup<GW>(fz, warp, GWARPS);
+  fused_setup<GW>(fz, warp, GWARPS, GWARPS + HELPER_WARPS);
 
   if (warp >= GWARPS) {
     ptx::reg_dec<GREGS_H>();

@@ -43,7 +43,7 @@ struct seam_handle {
   float* tw_misc = nullptr;           // bias0..3 (256,256,256,1024) | lin_wt (1024*256) | lin_b | bn_scale | bn_shift
   bool have_tower = false;
   // developer overrides, read once at seam_create (never consulted on the hot path)
-  int dbg_score_grid = 0, dbg_agg_grid = 0, dbg_cta_ns = 0, score_nseed = 4;
+  int dbg_score_grid = 0, dbg_agg_grid = 0, dbg_cta_ns = 0, dbg_no_tm = 0, score_nseed = 4;
   struct Span { int kernel; cudaEvent_t a, b; };
   std::vector<Span> spans;            // recorded while profiling
   std::vector<cudaEvent_t> free_events;
@@ -130,6 +130,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // (1+Tmax, Q, 256) with the caller's strides.  Returns whether the map is usable.
 static int encode_seq_map(seam_handle* h, const aggf::Params& p, int box_frames, CUtensorMap* tm) {
   memset(tm, 0, sizeof(*tm));
+  if (h->dbg_no_tm) return 0;
   if (!p.seq || p.Q <= 0 || (p.track_stride * 4) % 16 != 0 || (p.frame_stride * 4) % 16 != 0 || p.track_stride < 256 ||
       p.frame_stride < 256 || box_frames > p.Tmax)
     return 0;
@@ -238,6 +239,7 @@ int seam_create(seam_handle** out, int device) {
   h->dbg_score_grid = env_int("SEAM_DEBUG_SCORE_GRID", 0);
   h->dbg_agg_grid = env_int("SEAM_DEBUG_AGG_GRID", 0);
   h->dbg_cta_ns = env_int("SEAM_DEBUG_CTA_NS", 0);
+  h->dbg_no_tm = env_int("SEAM_DEBUG_AGG_NO_TM", 0);      // developer A/B: per-frame bulk copies instead of one tensor-map box
   h->score_nseed = env_int("SEAM_SCORE_NSEED", 4);
   // watchdog records live in host-mapped memory so that they survive a trapped launch: one buffer per
   // device for the life of the process (the device-side pointer must never dangle)
