@@ -276,16 +276,28 @@ __device__ __forceinline__ void filter16(const uint32_t (&r)[16], const float* c
     cgv[c4 * 4 + 2] = g4.z;
     cgv[c4 * 4 + 3] = g4.w;
   }
+  // acc + cg two columns per instruction (add.rn.f32x2: the same IEEE sums, half the issue slots), then the tags
+  float v[16];
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    unsigned long long s2;
+    asm("{\n"
+        ".reg .b64 a, b;\n"
+        "mov.b64 a, {%1, %2};\n"
+        "mov.b64 b, {%3, %4};\n"
+        "add.rn.f32x2 %0, a, b;\n"
+        "}\n"
+        : "=l"(s2)
+        : "r"(r[e]), "r"(r[e + 1]), "f"(cgv[e]), "f"(cgv[e + 1]));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v[e]), "=f"(v[e + 1]) : "l"(s2));
+  }
   float w[16];
-  w[0] = tagged_imm<Q0 + 0>(r[0], cgv[0], keep);
-  w[4] = tagged_imm<Q0 + 1>(r[4], cgv[4], keep);
-  w[8] = tagged_imm<Q0 + 2>(r[8], cgv[8], keep);
-  w[12] = tagged_imm<Q0 + 3>(r[12], cgv[12], keep);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    w[4 * q + 1] = tagged_reg(r[4 * q + 1], cgv[4 * q + 1], keep, tg.t1);
-    w[4 * q + 2] = tagged_reg(r[4 * q + 2], cgv[4 * q + 2], keep, tg.t2);
-    w[4 * q + 3] = tagged_reg(r[4 * q + 3], cgv[4 * q + 3], keep, tg.t3);
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=f"(w[4 * q]) : "f"(v[4 * q]), "r"(keep), "r"((uint32_t)(Q0 + q)));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=f"(w[4 * q + 1]) : "f"(v[4 * q + 1]), "r"(keep), "r"(tg.t1));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=f"(w[4 * q + 2]) : "f"(v[4 * q + 2]), "r"(keep), "r"(tg.t2));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=f"(w[4 * q + 3]) : "f"(v[4 * q + 3]), "r"(keep), "r"(tg.t3));
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
