@@ -610,7 +610,8 @@ def parity_check(pkg, eng, wl, res, e2e_idx, weights, world, rank, dev):
     par = "single GPU"
     if world > 1:
         par = (f"gallery sharded x{world}, tracks aggregated and lists merged by the rank that owns the query; exchange: " +
-               ("stores from inside the kernels into peer-mapped buffers + flag words (NVLink), no collective"
+               ("stores from inside the kernels into peer-mapped buffers + flag words (NVLink), no collective" +
+                ("; descriptors by NVSwitch multicast (one store per row reaches every rank)" if wl.peer.multicast else "")
                 if wl.peer is not None else "NCCL all-gathers" + wl.peer_note))
     out = {"_launch": launch, "_parallelism": par}
     g_full = wl.gal

@@ -245,7 +245,17 @@ typedef struct seam_exchange {
   uint32_t* flags[SEAM_MAX_WORLD];
   uint32_t* step;
   uint32_t* done;
+  /* optional (null: not used): the NVSwitch MULTICAST mapping of q_all -- one store to it lands in every rank's q_all
+   * (the switch replicates it), so a rank's descriptors leave its GPU once instead of world - 1 times */
+  float* q_all_mc;
+  /* the same for the merged rows (all three or none) */
+  float* final_score_mc;
+  float* final_margin_mc;
+  int32_t* final_idx_mc;
 } seam_exchange;
+
+/* sizeof(seam_exchange) as this library was built (device-free): a binding checks its own struct layout against it */
+size_t seam_exchange_sizeof(void);
 
 /* seam_aggregate for tracks [row0, row0 + Qlocal) of the step's Q queries (a rank may pass its tracks in several
  * calls, e.g. as they arrive from the host): descriptors go to rows row0.. of every rank's q_all; the call with

@@ -55,7 +55,7 @@ if peer is not None:
     if rank == 0:
         same2 = torch.equal(ix2, ix1) and torch.equal(mg2, mg1) and torch.equal(sc2, sc1)
         print(f"world={world}: in-kernel exchange vs single-GPU: eager identical={same2}, 4 graph replays with new queries "
-              f"identical={ok3}, steps done={peer.steps_done}, watchdog={eng.watchdog_records()}")
+              f"identical={ok3}, steps done={peer.steps_done}, multicast={peer.multicast}, watchdog={eng.watchdog_records()}")
         ok = ok and same2 and ok3
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)

@@ -62,16 +62,32 @@ def build_variant(name: str, defines) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/ -> libseam_b200.so (only when sources are newer). Returns the path."""
+    """Compile csrc/ -> libseam_b200.so (only when sources are newer). Returns the path.
+
+    Safe under several processes (one rank per GPU starting at once): the build is serialised by a lock file, the
+    library is written under a temporary name and renamed into place, so nobody ever maps a half-written file."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
-    with open(INFO_PATH, "w") as f:
-        f.write(source_hash())
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():             # another process built it while this one waited
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.tmp{os.getpid()}"
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+                  [os.path.join(CSRC, s) for s in SOURCES]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+            if verbose:
+                print(proc.stderr)
+            os.replace(tmp, LIB_PATH)
+            with open(INFO_PATH + ".tmp", "w") as f:
+                f.write(source_hash())
+            os.replace(INFO_PATH + ".tmp", INFO_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH

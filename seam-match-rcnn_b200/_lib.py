@@ -47,7 +47,8 @@ class SeamExchange(C.Structure):
                 ("final_score", C.c_void_p * SEAM_MAX_WORLD), ("final_margin", C.c_void_p * SEAM_MAX_WORLD),
                 ("final_idx", C.c_void_p * SEAM_MAX_WORLD),
                 ("flags", C.c_void_p * SEAM_MAX_WORLD),
-                ("step", C.c_void_p), ("done", C.c_void_p)]
+                ("step", C.c_void_p), ("done", C.c_void_p), ("q_all_mc", C.c_void_p),
+                ("final_score_mc", C.c_void_p), ("final_margin_mc", C.c_void_p), ("final_idx_mc", C.c_void_p)]
 
 
 class SeamWeightGrads(C.Structure):
@@ -82,6 +83,8 @@ def _declare(lib: C.CDLL) -> None:
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     lib.seam_abi_version.restype = i32
     lib.seam_abi_version.argtypes = []
+    lib.seam_exchange_sizeof.restype = sz
+    lib.seam_exchange_sizeof.argtypes = []
     lib.seam_create.restype = i32
     lib.seam_create.argtypes = [C.POINTER(vp), i32]
     lib.seam_destroy.restype = None

@@ -315,6 +315,7 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
   const int nbatch = (int)((n_cta + NB - 1) / NB);
 #endif
   const float ms_inv = p.fold[Fold::CONSTS + 9];        // 1 / S
+  const bool mc = p.x_on && p.x.world > 1 && p.x.q_all_mc != nullptr;
   const uint32_t rt_addr = ptx::smem_u32(fz + OFF_RT), tail_addr = ptx::smem_u32(fz + OFF_TAIL);
   constexpr uint32_t idesc = ptx::umma_idesc(0 /*fp16*/, 128, NB);
 
@@ -407,7 +408,13 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
         o[0] = v0;
         o[128] = v1;
         if (p.x_on) {
-          if constexpr (POOL_SMEM) {                      // the finished row replaces pooled' in the staging tile (see below)
+          if (mc) {
+            // NVSwitch multicast: ONE store (a 128-byte line per warp) lands in every rank's q_all -- the switch
+            // replicates it, the descriptors leave this GPU once instead of world - 1 times
+            float* mo = p.x.q_all_mc + ((size_t)(xstep & 1u) * p.x.Q + (size_t)p.x_row0 + (size_t)track) * D + ch;
+            mo[0] = v0;
+            mo[128] = v1;
+          } else if constexpr (POOL_SMEM) {               // the finished row replaces pooled' in the staging tile (see below)
             float* pw = reinterpret_cast<float*>(fz + OFF_POOL + buf * POOL_BYTES);
             pw[t * D + ch] = v0;
             pw[t * D + 128 + ch] = v1;
@@ -424,11 +431,11 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
       }
     }
     if constexpr (POOL_SMEM) {
-      // Sharded search: the batch's finished rows go to the other ranks as 1 KB bulk async copies shared -> peer
-      // global (NVLink), one (track, destination) pair per helper thread: the copy engine does the remote
-      // writes, no warp waits on NVLink write credits (plain stores from the four helper warps took ~40 us
+      // Sharded search without multicast: the batch's finished rows go to the other ranks as 1 KB bulk async copies
+      // shared -> peer global (NVLink), one (track, destination) pair per helper thread: the copy engine does the
+      // remote writes, no warp waits on NVLink write credits (plain stores from the four helper warps took ~40 us
       // for 13 MB at 8 GPUs).
-      if (p.x_on && p.x.world > 1) {
+      if (p.x_on && p.x.world > 1 && !mc) {
         ptx::fence_proxy_async_smem();                   // generic writes of the rows -> visible to the copy engine
         ptx::named_bar_sync(1, HELPER_WARPS * 32);       // all four channel quarters of every row are in place
         const int h = hw * 32 + lane, t = h >> 3, r = h & 7;
@@ -447,7 +454,7 @@ __device__ __forceinline__ void helper_role(const Params& p, uint8_t* fz, int hw
     if (hw == 0 && b == 3) SEAM_TL3(p, 4);
   }
   if constexpr (POOL_SMEM) {
-    if (p.x_on && p.x.world > 1) {                       // this thread's remote rows are written before the CTA is counted
+    if (p.x_on && p.x.world > 1 && !mc) {                // this thread's remote rows are written before the CTA is counted
       ptx::bulk_wait_all();
       ptx::fence_proxy_async_all();
     }
@@ -734,13 +741,13 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
 #endif
         Vec8 x[TR];
 #pragma unroll
-        for (int t0 = 0; t0 < TR; t0 += 4) {
-          const int nf = TR - t0 < 4 ? TR - t0 : 4;     // frames in this group (compile time after unrolling)
-          float acc[16];
+        for (int t0 = 0; t0 < TR; t0 += 8) {            // 8 frames = 32 totals per butterfly: the 5 dependent shuffle rounds
+          const int nf = TR - t0 < 8 ? TR - t0 : 8;     // of a butterfly are the phase's latency (compile time after unrolling)
+          float acc[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+          for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int t = t0 + u;
             if (u < nf) {
               if (FULL || t < len) x[t] = load_vec8(xs + t * D, lane);
@@ -751,16 +758,21 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
               acc[4 * u + 3] = dot8(x[t], ug);
             }
           }
-          if (nf > 2) {
-            const float tot = treduce<16>(acc, lane);
-            if (lane < 4 * nf) scal[4 * t0 + lane] = tot + my_const;
+          float tot;
+          if (nf > 4) {
+            tot = treduce<32>(acc, lane);
+          } else if (nf > 2) {
+            float a16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a16[i] = acc[i];
+            tot = treduce<16>(a16, lane);
           } else {
             float a8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) a8[i] = acc[i];
-            const float tot = treduce<8>(a8, lane);
-            if (lane < 4 * nf) scal[4 * t0 + lane] = tot + my_const;
+            tot = treduce<8>(a8, lane);
           }
+          if (lane < 4 * nf) scal[4 * t0 + lane] = tot + my_const;
         }
         SEAM_WPH(2);
         if constexpr (SLOTS == 1) {
@@ -1041,7 +1053,7 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
     const float my_const = comp == 0 ? fold[Fold::CONSTS + 0] : comp == 2 ? fold[Fold::CONSTS + 1]
                          : comp == 3 ? fold[Fold::CONSTS + 2] : 0.f;
     // where this lane's butterfly total (component comp of frame SF0 + t0) goes: the T x T loops read PAIRS of frames
-    const int SF0 = FB * wg + ((lane >> 2) & 3);
+    const int SF0 = FB * wg + (lane >> 2);
     float* const sc_dst = (comp < 2 ? &gs.ad[0][0] : &gs.bc[0][0]) + (SF0 >> 1) * 4 + ((comp & 1) << 1) + (SF0 & 1);
 
 #ifndef SEAM_AGG_HELPER_INIT
@@ -1060,14 +1072,15 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
       SEAM_PH(1);
       const int nw = max(0, min(len - FB * wg, FB));
 
-      // ---- my 16 frames -> registers (zeros past the block's end), four dots per frame, totals of 4 frames per butterfly
+      // ---- my 16 frames -> registers (zeros past the block's end), four dots per frame, the 32 totals of 8 frames per
+      // butterfly (five dependent shuffle rounds per 8 frames instead of per 4: the rounds are the phase's latency)
       const uint32_t raw_next = peek(track + stride);
       Vec8 x[FB];
 #pragma unroll
-      for (int t0 = 0; t0 < FB; t0 += 4) {
-        float acc[16];
+      for (int t0 = 0; t0 < FB; t0 += 8) {
+        float acc[32];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int t = t0 + u;
           x[t] = load_vec8(xs + t * D, lane);
           acc[4 * u + 0] = dot8(x[t], ut);
@@ -1075,9 +1088,9 @@ aggregate_fused_group_kernel(const __grid_constant__ CUtensorMap tmSeq, const Pa
           acc[4 * u + 2] = dot8(x[t], up);
           acc[4 * u + 3] = dot8(x[t], ug);
         }
-        const float tot = treduce<16>(acc, lane);
+        const float tot = treduce<32>(acc, lane);
         // frame F = FB wg + t0 + (lane >> 2): a, d -> ad[F / 2][F % 2 (+ 2)], b, c -> bc[...], zero past the track's end
-        if (lane < 16) sc_dst[2 * t0] = (comp < 2 || SF0 + t0 < len) ? tot + my_const : 0.f;
+        sc_dst[2 * t0] = (comp < 2 || SF0 + t0 < len) ? tot + my_const : 0.f;
       }
       SEAM_PH(2);
       // the buffer is free again: fetch this warp's block of the group's next track

@@ -37,6 +37,10 @@ struct Exchange {                        // device-side image of seam_exchange (
   uint32_t* flags[MAX_WORLD];            // (NKIND, MAX_WORLD) words on each rank
   uint32_t* step;                        // local: number of the step in progress (starts at 1)
   uint32_t* done;                        // local: NKIND CTA-completion counters (zero between kernels)
+  float* q_all_mc;                       // NVSwitch multicast mapping of q_all (null: none): one store reaches every rank
+  float* final_score_mc;                 // ... of the merged rows (all three or none)
+  float* final_margin_mc;
+  int32_t* final_idx_mc;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {

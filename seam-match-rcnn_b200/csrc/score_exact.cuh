@@ -6,6 +6,7 @@
 //   l_c = sum_k W[c][k] * (q_k - g_k)^2 + b_c   (models/match_head.py:161-162,
 //   evaluate_movingfashion.py:263-264), score = softmax(l)[1] (:265-267).
 #pragma once
+#include <type_traits>
 #include <climits>
 #include <cstdint>
 #include <cuda_fp16.h>
@@ -277,7 +278,7 @@ __device__ __forceinline__ void rescore_merge32(const uint2* wb, int begin, int 
   wsort::merge32<true>(cv, cidx, lane);
 }
 
-// (launch bounds of 5 CTAs per SM = 48 registers were measured: 168 bytes of spills, 70 -> 83 us)
+// (other occupancies were measured: 5 CTAs per SM = 48 registers, 168 bytes of spills: 70 -> 83 us; 3 CTAs = 80 registers: 78 us)
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   __shared__ uint2 wbuf[8][RESCORE_WBUF];
   __shared__ uint4 qbuf[8][64];
@@ -310,18 +311,20 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     // first) also bounds the 32nd best -- with ~40 instead of ~300 items above it.
     const int nval = nl_valid * 16;
     const float* gmp = p.gmax + (size_t)qi * p.nlists * 16;
-    uint32_t key[8];
+    // NK keys per lane: 4 when the row's sweep was shared by at most two CTAs (128 maxima: the eval sizes), else 8
+    auto start_cut = [&](auto nk_tag) {
+      constexpr int NK = decltype(nk_tag)::value;
+      uint32_t key[NK];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = lane + 32 * u;
-      key[u] = i < nval ? ptx::float_to_ordered(gmp[i]) : 0u;
-    }
-    if (nval <= 256) {
+      for (int u = 0; u < NK; ++u) {
+        const int i = lane + 32 * u;
+        key[u] = i < nval ? ptx::float_to_ordered(gmp[i]) : 0u;
+      }
       // The answer lies between lo = the smallest lane maximum (32 distinct maxima are >= it) and
       // hi = the largest maximum: only the bits below their common prefix need deciding.
       uint32_t lmax = key[0];
 #pragma unroll
-      for (int j = 1; j < 8; ++j) lmax = max(lmax, key[j]);
+      for (int j = 1; j < NK; ++j) lmax = max(lmax, key[j]);
       const uint32_t hi = __reduce_max_sync(ptx::FULL_MASK, lmax);
       const uint32_t lo = __reduce_min_sync(ptx::FULL_MASK, lmax);
       uint32_t K = lo;
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
           const uint32_t T = K | (1u << b);
           uint32_t c = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < NK; ++j)
             asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p add.u32 %0, %0, 1;\n}\n" : "+r"(c) : "r"(key[j]), "r"(T));
           if (__reduce_add_sync(ptx::FULL_MASK, c) >= 32u) K = T;
         }
@@ -342,7 +345,9 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
         cut = tt;
         cut_lo = nextafterf(tt, -INFINITY);
       }
-    }
+    };
+    if (nval <= 128) start_cut(std::integral_constant<int, 4>{});
+    else if (nval <= 256) start_cut(std::integral_constant<int, 8>{});
   }
   // A record is a quad {w0,w1,w2,w3} of adjacent gallery rows (score_tc.cuh): the 6 low mantissa bits of
   // w0 hold the quad's position inside its 64-column quarter, those of w1..w3 the gallery tile index;
@@ -1100,10 +1105,16 @@ __global__ void __launch_bounds__(256) merge_sharded_kernel(const xchg::Exchange
       const int ii = ok ? id : -1;
       if (x.final_score[0]) {
         const size_t o = (size_t)(x.q_lo[x.rank] + qo) * k + lane;
-        for (int r = 0; r < x.world; ++r) {
-          x.final_score[r][o] = sc;
-          x.final_margin[r][o] = dm;
-          x.final_idx[r][o] = ii;
+        if (x.final_score_mc) {               // NVSwitch multicast: one store reaches every rank's copy
+          x.final_score_mc[o] = sc;
+          x.final_margin_mc[o] = dm;
+          x.final_idx_mc[o] = ii;
+        } else {
+          for (int r = 0; r < x.world; ++r) {
+            x.final_score[r][o] = sc;
+            x.final_margin[r][o] = dm;
+            x.final_idx[r][o] = ii;
+          }
         }
       } else {
         const size_t o = (size_t)qo * k + lane;

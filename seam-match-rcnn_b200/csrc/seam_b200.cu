@@ -195,12 +195,19 @@ static int import_exchange(seam_handle* h, const seam_exchange* x, xchg::Exchang
   }
   e->step = x->step;
   e->done = x->done;
+  e->q_all_mc = x->world > 1 ? x->q_all_mc : nullptr;
+  const bool final_mc = x->world > 1 && have_final && x->final_score_mc && x->final_margin_mc && x->final_idx_mc;
+  e->final_score_mc = final_mc ? x->final_score_mc : nullptr;
+  e->final_margin_mc = final_mc ? x->final_margin_mc : nullptr;
+  e->final_idx_mc = final_mc ? x->final_idx_mc : nullptr;
   return SEAM_OK;
 }
 
 extern "C" {
 
-int seam_abi_version(void) { return 2; }
+int seam_abi_version(void) { return 3; }
+
+size_t seam_exchange_sizeof(void) { return sizeof(seam_exchange); }
 
 int seam_create(seam_handle** out, int device) {
   if (!out) return fail(nullptr, SEAM_ERR_BAD_ARG, "seam_create: out is null");

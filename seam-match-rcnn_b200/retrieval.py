@@ -306,6 +306,10 @@ class PeerExchange:
                 h = symm.rendezvous(t, self.group)
                 self._bufs[n] = t
                 self._peers[n] = [t if r == self.rank else h.get_buffer(r, shapes[n], dtypes[n]) for r in range(self.world)]
+                # multicast pays when a row has several destinations (N = 8: step -4 %); with one peer it only adds the
+                # copy the switch reflects back (measured slower at N = 2)
+                self._mc = getattr(self, "_mc", {})
+                self._mc[n] = self._multicast_address(h, t) if self.world > 2 else 0
             torch.cuda.synchronize(dev)
             dist.barrier(self.group)                       # nobody signals into flags a peer has not zeroed yet
         self._step = torch.ones(1, dtype=torch.int32, device=dev)
@@ -329,6 +333,32 @@ class PeerExchange:
                 arr[r] = t.data_ptr()
         x.step = self._step.data_ptr()
         x.done = self._done.data_ptr()
+        mc = getattr(self, "_mc", {})
+        x.q_all_mc = mc.get("q_all", 0) or None
+        fin = [mc.get(n, 0) for n in ("final_score", "final_margin", "final_idx")]
+        x.final_score_mc, x.final_margin_mc, x.final_idx_mc = fin if all(fin) else (None, None, None)
+
+    @staticmethod
+    def _multicast_address(handle, t: torch.Tensor) -> int:
+        """Address of ``t`` in the NVSwitch multicast mapping of its symmetric allocation (0: none -- no NVLS on this
+        box, or switched off with SEAM_NO_MULTICAST=1).  A store to it lands in every rank's copy of the tensor."""
+        import os
+        if os.environ.get("SEAM_NO_MULTICAST", "0") == "1":
+            return 0
+        try:
+            base = int(handle.multicast_ptr)
+            local = int(handle.buffer_ptrs[handle.rank])
+        except Exception:                                    # noqa: BLE001 -- an optimisation, never an error
+            return 0
+        off = t.data_ptr() - local
+        if base == 0 or off < 0 or off + t.numel() * t.element_size() > int(handle.buffer_size):
+            return 0
+        return base + off
+
+    @property
+    def multicast(self) -> bool:
+        """Whether the descriptors travel by NVSwitch multicast (one store per row instead of world - 1)."""
+        return bool(getattr(self, "_mc", {}).get("q_all", 0))
 
     @property
     def final(self):

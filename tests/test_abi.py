@@ -18,7 +18,10 @@ def test_library_builds_and_exports_all_declared_symbols():
     assert len(declared) >= 17
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/seam_b200.h but not exported"
-    assert lib.seam_abi_version() == 2
+    assert lib.seam_abi_version() == 3
+    from seam_match_rcnn_b200._lib import SeamExchange
+    import ctypes
+    assert ctypes.sizeof(SeamExchange) == lib.seam_exchange_sizeof(), "ctypes image of struct seam_exchange is out of step with the header"
     # pure host helpers are callable without a device
     assert lib.seam_aggregate_workspace_bytes(1000) >= 256       # the fused kernel needs no workspace
     assert lib.seam_nlb_workspace_bytes(3, 10) >= 2 * 30 * 256 * 4
