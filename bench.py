@@ -641,6 +641,8 @@ def parity_check(pkg, eng, wl, res, e2e_idx, weights, world, rank, dev):
                 "topk_identical_up_to_ties": bool(err <= TOL_MARGIN and ties_ok),
                 "rows_differing_from_oracle_order": int(differs.any(1).sum()),
                 "planted_match_in_topk_frac": planted_in_topk,
+                "planted_match_note": "random-init `last` (SURVEY 8(d): module default init): the class-1 score is not a "
+                                      "similarity, so the planted rows exercise cancellation in the expanded form, not top-1",
                 "e2e_indices_equal_device_run": bool(torch.equal(e2e_idx[wl.qlo:wl.qhi], ix.cpu()[wl.qlo:wl.qhi]))})
     if world > 1 and g_full is not wl.gal:
         s1, m1, i1 = pkg.search(eng, wl.seq, wl.mask, g_full, wl.k)

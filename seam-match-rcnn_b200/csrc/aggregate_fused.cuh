@@ -733,10 +733,10 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         constexpr bool FULL = decltype(full_tag)::value;
         // ---- frames -> registers, four dots per frame; every 4 frames a transposing butterfly leaves
         // the 16 totals (a, d, b, c of 4 frames) in lanes 0..15
-#ifndef SEAM_AGG_DIAG_NO_PUBLISH
         // the track's slot in the batch under construction: the shared-memory atomic's round trip (~200 cycles) is
         // started here and used after the weighted sums
         unsigned ticket = 0u;
+#ifndef SEAM_AGG_DIAG_NO_PUBLISH
         if (lane == 0) ticket = atomicAdd(&meta->next_slot, 1u);
 #endif
         Vec8 x[TR];
