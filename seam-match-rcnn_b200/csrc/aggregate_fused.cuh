@@ -777,7 +777,12 @@ aggregate_fused_warp_kernel(const __grid_constant__ CUtensorMap tmSeq, const Par
         SEAM_WPH(2);
         if constexpr (SLOTS == 1) {
           __syncwarp();                                // all lanes hold their frames in registers:
-          if (lane == 0) ptx::mbar_arrive(&empty_all[warp]);   // the loader warp may refill the buffer
+          if constexpr (LOADER) {
+            if (lane == 0) ptx::mbar_arrive(&empty_all[warp]);   // the loader warp may refill the buffer
+          } else {
+            issue(track + stride, 0, raw_next);        // no loader warp (TR = 16): the producer refills it itself
+            raw_next = peek(track + 2 * stride);
+          }
         }
         __syncwarp();
         SEAM_WPH(3);

@@ -74,6 +74,23 @@ def test_aggregate_every_kernel_variant(Q, T, ragged, weights, engine):
         assert torch.equal(out.cpu()[single], seq[1][single])
 
 
+@pytest.mark.parametrize("Q,T,ragged", [(7500, 4, (1, 4)), (5000, 10, None), (5200, 9, (0, 9)), (3700, 16, None),
+                                        (3600, 14, (2, 14)), (1900, 32, None), (1850, 27, (17, 27)), (950, 64, None),
+                                        (930, 50, (33, 50))])
+def test_aggregate_many_tracks_per_warp(Q, T, ragged, weights, engine):
+    """Every kernel variant with MORE tracks than producers (three or more iterations per producer warp: buffers are
+    refilled -- by the loader warp at T <= 10, by the producers themselves otherwise -- batches are recycled), against
+    the oracle on a sample of tracks; lens and mask paths agree bit for bit."""
+    seq, mask, lens = so.synth_tracks(Q, T, seed=3 * Q + T, ragged=ragged)
+    out = engine.aggregate(seq.to(DEV), mask.to(DEV))
+    out2 = engine.aggregate(seq.to(DEV), None, lens=torch.as_tensor(lens))
+    assert torch.equal(out, out2)
+    rows = torch.from_numpy(np.random.RandomState(Q).choice(Q, 160, replace=False)).sort().values
+    rows = torch.cat([rows, torch.tensor([0, Q - 1])]).unique()
+    ref, _ = so.aggregate_tracks(seq[:, rows], mask[rows], weights)
+    assert (out.cpu()[rows] - ref).abs().max() <= TOL_EMB
+
+
 def test_aggregate_empty_and_limits(engine):
     assert engine.aggregate(torch.zeros(1, 5, 256, device=DEV)).abs().sum() == 0     # Tmax == 0
     assert engine.aggregate(torch.zeros(4, 0, 256, device=DEV)).shape == (0, 256)    # Q == 0
