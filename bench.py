@@ -353,7 +353,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, align=None):
+        """ms per step, device-timed, max over ranks.  `align` (N > 1): a cross-rank barrier KERNEL enqueued right
+        before the start event, so that every rank's GPU enters the step at the same moment -- the ranks wait for
+        each other's data inside the kernels, and without it the host's launch skew between the processes (tens of
+        microseconds on a loaded box) is counted as step time."""
         for _ in range(warmup):
             fn()
         barrier()
@@ -361,6 +365,8 @@ def run_ours(args):
         for _ in range(steps):
             flush.fill_(1)                   # evict L2 between timed iterations (not timed)
             barrier()
+            if align is not None:
+                align()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
@@ -401,7 +407,8 @@ def run_ours(args):
     warmup = max(args.warmup, 3)
     sampler = ClockSampler(local)                             # samples through the device-timed AND the e2e timed regions
     sampler.start()
-    ms = timed(wl.step, args.steps, warmup)
+    align = wl.peer.device_barrier if (world > 1 and wl.peer is not None) else None
+    ms = timed(wl.step, args.steps, warmup, align)
 
     # ---- end to end from pinned host memory through the package's host-facing entry points
     # (retrieval.search_host / HostTrackStream): the rank's tracks cross PCIe in NCHUNK slices on a copy stream;
@@ -563,7 +570,7 @@ def run_ours(args):
     for name, kw, desc in plan:
         w2 = Workload(pkg, eng, dev, world, rank, name, **kw)
         w2.capture()
-        ms2 = timed(w2.step, sub_steps, 3)
+        ms2 = timed(w2.step, sub_steps, 3, w2.peer.device_barrier if (world > 1 and w2.peer is not None) else None)
         kern2, _ = kernel_times(w2, sub_steps)
         rec = stage_record(w2, kern2, ms2, peaks)
         rec["workload"] = desc
@@ -584,6 +591,9 @@ def run_ours(args):
                        "launch": parity.pop("_launch"),
                        "e2e_launch": "one CUDA graph replay per step (H2D, kernels, D2H)" if e2e_graph is not None else "eager",
                        "host_numa_node": numa,
+                       "rank_alignment": ("a cross-rank barrier kernel (symmetric-memory signal pads) precedes the start event of "
+                                          "every timed step: the GPUs enter the step together, host launch skew is not counted")
+                                         if align is not None else None,
                        "parallelism": parity.pop("_parallelism")},
             "queries_per_sec": Q / (ms * 1e-3),
             "e2e": {"value": Q * G / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

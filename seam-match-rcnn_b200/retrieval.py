@@ -305,6 +305,7 @@ class PeerExchange:
                 t.zero_()
                 h = symm.rendezvous(t, self.group)
                 self._bufs[n] = t
+                self._handle = h
                 self._peers[n] = [t if r == self.rank else h.get_buffer(r, shapes[n], dtypes[n]) for r in range(self.world)]
                 # multicast pays when a row has several destinations (N = 8: step -4 %); with one peer it only adds the
                 # copy the switch reflects back (measured slower at N = 2)
@@ -354,6 +355,14 @@ class PeerExchange:
         if base == 0 or off < 0 or off + t.numel() * t.element_size() > int(handle.buffer_size):
             return 0
         return base + off
+
+    def device_barrier(self) -> None:
+        """Enqueue a cross-rank barrier KERNEL on the current stream (symmetric-memory signal pads): every rank's
+        stream passes it at the same moment.  Not part of the search (the kernels order themselves by flag words);
+        measurements use it so that a step timed on the device does not include the host's launch skew between ranks."""
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            h.barrier(channel=0)
 
     @property
     def multicast(self) -> bool:
