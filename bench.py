@@ -251,6 +251,7 @@ class Workload:
             self.retr = pkg.ShardedRetriever(eng, self.gallery, self.glo)
         self.graph = None
         self.graph_out = None
+        self.stamps = None
 
     # one pass of the hot path, inputs resident in HBM
     def hot_path(self):
@@ -281,7 +282,17 @@ class Workload:
             dist.barrier()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            if self.world > 1:
+                # N > 1: the ranks wait for each other's data inside the kernels, so a step must START at the same
+                # moment on every GPU or the host's launch skew between the rank processes is measured as step time.
+                # The replayed graph is [cross-rank barrier kernel, time stamp, the step, time stamp]: the barrier node
+                # aligns the GPUs, the step is timed between the two stamps (%globaltimer, one-thread kernels).
+                self.stamps = torch.zeros(2, dtype=torch.int64, device=dev)
+                self.peer.device_barrier()
+                self.eng.device_stamp(self.stamps, 0)
             self.graph_out = self.hot_path()
+            if self.world > 1:
+                self.eng.device_stamp(self.stamps, 1)
 
     def step(self):
         if self.graph is not None:
@@ -353,11 +364,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, align=None):
-        """ms per step, device-timed, max over ranks.  `align` (N > 1): a cross-rank barrier KERNEL enqueued right
-        before the start event, so that every rank's GPU enters the step at the same moment -- the ranks wait for
-        each other's data inside the kernels, and without it the host's launch skew between the processes (tens of
-        microseconds on a loaded box) is counted as step time."""
+    def timed(fn, steps, warmup, stamps=None):
+        """ms per step, device-timed, max over ranks: CUDA events around fn() on the launching stream -- or, with
+        `stamps` (the sharded step's graph: [cross-rank barrier kernel, stamp, step, stamp]), the difference of the two
+        device time stamps the graph itself wrote (events cannot be recorded between the nodes of a replayed graph)."""
         for _ in range(warmup):
             fn()
         barrier()
@@ -365,14 +375,12 @@ def run_ours(args):
         for _ in range(steps):
             flush.fill_(1)                   # evict L2 between timed iterations (not timed)
             barrier()
-            if align is not None:
-                align()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
             b.record()
             barrier()
-            total += a.elapsed_time(b)
+            total += (float(stamps[1] - stamps[0]) * 1e-6) if stamps is not None else a.elapsed_time(b)
         t = torch.tensor([total / steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -407,8 +415,10 @@ def run_ours(args):
     warmup = max(args.warmup, 3)
     sampler = ClockSampler(local)                             # samples through the device-timed AND the e2e timed regions
     sampler.start()
-    align = wl.peer.device_barrier if (world > 1 and wl.peer is not None) else None
-    ms = timed(wl.step, args.steps, warmup, align)
+    ms = timed(wl.step, args.steps, warmup, wl.stamps if wl.graph is not None else None)
+    rank_alignment = ("the replayed graph is [cross-rank barrier kernel, device time stamp, step, device time stamp]: the GPUs "
+                      "enter the step together and the step is timed between the stamps (host launch skew is not step time)"
+                      if (wl.graph is not None and wl.stamps is not None) else None)
 
     # ---- end to end from pinned host memory through the package's host-facing entry points
     # (retrieval.search_host / HostTrackStream): the rank's tracks cross PCIe in NCHUNK slices on a copy stream;
@@ -570,7 +580,7 @@ def run_ours(args):
     for name, kw, desc in plan:
         w2 = Workload(pkg, eng, dev, world, rank, name, **kw)
         w2.capture()
-        ms2 = timed(w2.step, sub_steps, 3, w2.peer.device_barrier if (world > 1 and w2.peer is not None) else None)
+        ms2 = timed(w2.step, sub_steps, 3, w2.stamps if w2.graph is not None else None)
         kern2, _ = kernel_times(w2, sub_steps)
         rec = stage_record(w2, kern2, ms2, peaks)
         rec["workload"] = desc
@@ -591,9 +601,7 @@ def run_ours(args):
                        "launch": parity.pop("_launch"),
                        "e2e_launch": "one CUDA graph replay per step (H2D, kernels, D2H)" if e2e_graph is not None else "eager",
                        "host_numa_node": numa,
-                       "rank_alignment": ("a cross-rank barrier kernel (symmetric-memory signal pads) precedes the start event of "
-                                          "every timed step: the GPUs enter the step together, host launch skew is not counted")
-                                         if align is not None else None,
+                       "rank_alignment": rank_alignment,
                        "parallelism": parity.pop("_parallelism")},
             "queries_per_sec": Q / (ms * 1e-3),
             "e2e": {"value": Q * G / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

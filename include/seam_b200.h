@@ -54,6 +54,11 @@ uint64_t seam_launch_count(const seam_handle* h);
  * out and returns their number (0 in normal operation); works after the context has been lost. */
 int seam_watchdog_read(const seam_handle* h, uint32_t* out, int max_records);
 
+/* Writes the device's nanosecond timer (%globaltimer) to *dst (device memory) when the stream gets there: a one-thread
+ * kernel, graph-capturable -- how bench.py times a sharded step BETWEEN graph nodes (CUDA events cannot be recorded
+ * inside a replayed graph), after the node that aligns the ranks. */
+int seam_device_stamp(seam_handle* h, uint64_t* dst, void* stream);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, the library brackets each
  * of its named kernels with CUDA events on the launching stream.  seam_profile_read waits
  * for the recorded events of one kernel, returns their summed duration and count, and

@@ -93,6 +93,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.seam_last_error.argtypes = [vp]
     lib.seam_launch_count.restype = C.c_uint64
     lib.seam_launch_count.argtypes = [vp]
+    lib.seam_device_stamp.restype = i32
+    lib.seam_device_stamp.argtypes = [vp, vp, vp]
     lib.seam_watchdog_read.restype = i32
     lib.seam_watchdog_read.argtypes = [vp, C.POINTER(C.c_uint32), i32]
     lib.seam_profile_enable.restype = i32

@@ -203,6 +203,8 @@ static int import_exchange(seam_handle* h, const seam_exchange* x, xchg::Exchang
   return SEAM_OK;
 }
 
+__global__ void device_stamp_kernel(uint64_t* dst) { *dst = ptx::globaltimer_ns(); }
+
 extern "C" {
 
 int seam_abi_version(void) { return 3; }
@@ -320,6 +322,13 @@ int seam_watchdog_read(const seam_handle* h, uint32_t* out, int max_records) {
   if (n > max_records) n = max_records;
   for (int i = 0; i < n * 8; ++i) out[i] = w[8 + i];
   return n;
+}
+
+int seam_device_stamp(seam_handle* h, uint64_t* dst, void* stream) {
+  if (!h || !dst) return SEAM_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  device_stamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(dst);
+  return SEAM_OK;
 }
 
 const char* seam_last_error(const seam_handle* h) { return h ? h->err : g_create_err; }

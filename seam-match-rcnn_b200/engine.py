@@ -104,6 +104,12 @@ class SeamEngine:
             t = t.to(device=self.device, dtype=torch.float32).contiguous()
         return t
 
+    def device_stamp(self, stamps: torch.Tensor, index: int) -> None:
+        """Enqueue a one-thread kernel that writes the device's nanosecond timer into ``stamps[index]`` (int64, on this
+        device) -- graph-capturable: timing between the nodes of a replayed graph (``seam_device_stamp``)."""
+        assert stamps.dtype == torch.int64 and stamps.device == self.device
+        self._check(self._lib.seam_device_stamp(self._h, stamps.data_ptr() + 8 * int(index), self._stream()))
+
     def watchdog_records(self):
         """Records left by device-side wait watchdogs (empty in normal operation): a list of
         ``{tag, block, thread, barrier, parity}``; readable even after a failed launch."""
