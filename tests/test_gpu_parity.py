@@ -527,3 +527,30 @@ def test_score_topk_in_query_slabs(weights, engine, monkeypatch):
     monkeypatch.setattr(eng_mod, "SCORE_WS_LIMIT", 16 << 20)
     slabs = engine.score_topk(q, gal, 20)
     assert all(torch.equal(a, b) for a, b in zip(whole, slabs))
+
+
+def test_device_stamp_between_graph_nodes(engine):
+    """seam_device_stamp: the device's nanosecond timer written by a graph node -- how bench.py times a sharded step
+    between the nodes of a replayed graph.  Stamps grow, and bracket the work between them."""
+    st = torch.zeros(3, dtype=torch.int64, device=DEV)
+    x = torch.randn(1 << 24, device=DEV)
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream(DEV))
+    with torch.cuda.stream(side):
+        x.sum()
+        engine.device_stamp(st, 0)
+    torch.cuda.current_stream(DEV).wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        engine.device_stamp(st, 0)
+        y = x.sum()
+        engine.device_stamp(st, 1)
+        z = (x * 2).sum() + y
+        engine.device_stamp(st, 2)
+    for _ in range(2):
+        g.replay()
+        torch.cuda.synchronize()
+        a, b, c = (int(v) for v in st.cpu())
+        assert 0 < a < b < c
+        assert (c - a) < 50_000_000                    # two reductions over 64 MB: far below 50 ms
