@@ -246,17 +246,19 @@ __device__ __forceinline__ void store_r2(uint8_t* rt, int pos, int c, float r0, 
 template <int NWARPS, int INFLIGHT>
 __device__ __forceinline__ void load_m_tmem(const Params& p, Meta* meta, int warp, int lane) {
   constexpr int NPART = NWARPS / 4, NCHUNK = 16 + 2 * (KT / 32);
+  static_assert((KT / 2) % 4 == 0, "four columns per 16-byte load");
   const int part = warp >> 2, quarter = warp & 3;
   const uint32_t lane_base = meta->tmem_base + ((uint32_t)(quarter * 32) << 16);
-  const uint32_t* f32 = reinterpret_cast<const uint32_t*>(p.fold) + quarter * 32 + lane;
-  auto locate = [&](int c, const uint32_t*& src, uint32_t& col) {
+  // the images are [column / 4][row][column % 4] words (fold.cuh): four columns of this lane's row per 16-byte load
+  const uint4* f128 = reinterpret_cast<const uint4*>(p.fold) + quarter * 32 + lane;
+  auto locate = [&](int c, const uint4*& src, uint32_t& col) {
     if (c < 16) {
       const int h = c >> 3, c0 = (c & 7) * 16;
-      src = f32 + Fold::M1_IMG + (h * 128 + c0) * 128;
+      src = f128 + Fold::M1_IMG / 4 + ((h * 128 + c0) >> 2) * 128;
       col = COL_M1 + h * 128 + c0;
     } else {
       const int cc = c - 16, h = cc / (KT / 32), c0 = (cc % (KT / 32)) * 16;
-      src = f32 + Fold::M2_IMG + (h * (KT / 2) + c0) * 128;
+      src = f128 + Fold::M2_IMG / 4 + ((h * (KT / 2) + c0) >> 2) * 128;
       col = COL_M2 + h * (KT / 2) + c0;
     }
   };
@@ -265,11 +267,17 @@ __device__ __forceinline__ void load_m_tmem(const Params& p, Meta* meta, int war
     uint32_t v[INFLIGHT][16], col[INFLIGHT];
 #pragma unroll
     for (int u = 0; u < INFLIGHT; ++u) {
-      const uint32_t* src;
+      const uint4* src;
       const int cu = c + u * NPART;
       locate(cu < NCHUNK ? cu : c, src, col[u]);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[u][j] = __ldg(src + j * 128);
+      for (int j = 0; j < 4; ++j) {
+        const uint4 w = __ldg(src + j * 128);
+        v[u][4 * j + 0] = w.x;
+        v[u][4 * j + 1] = w.y;
+        v[u][4 * j + 2] = w.z;
+        v[u][4 * j + 3] = w.w;
+      }
     }
 #pragma unroll
     for (int u = 0; u < INFLIGHT; ++u)

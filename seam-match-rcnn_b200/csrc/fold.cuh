@@ -160,9 +160,10 @@ __global__ void fold_m16_kernel(float* __restrict__ fold) {
   if (k & 1) return;
   unsigned* f = reinterpret_cast<unsigned*>(fold);
   const int h = o >> 7, row = o & 127, c = k >> 1;
-  f[Fold::M1_IMG + (h * 128 + c) * 128 + row] = u1 | (p1 << 16);
+  // images: [column / 4][row 0..127][column % 4] words -- a lane fetches four columns of its row with one 16-byte load
+  f[Fold::M1_IMG + ((h * 128 + c) >> 2) * 512 + row * 4 + (c & 3)] = u1 | (p1 << 16);
   if (k < Fold::M2_KT) {
-    f[Fold::M2_IMG + (h * (Fold::M2_KT / 2) + c) * 128 + row] = u2 | (p2 << 16);
+    f[Fold::M2_IMG + ((h * (Fold::M2_KT / 2) + c) >> 2) * 512 + row * 4 + (c & 3)] = u2 | (p2 << 16);
   } else {
     constexpr int KS = 256 - Fold::M2_KT;            // 32 fp16 = 64-byte rows, SWIZZLE_64B: chunk ^= (row >> 1) & 3
     const int kk = k - Fold::M2_KT;
