@@ -540,12 +540,16 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const ExactParams p) {
   const int nrows = p.count ? *p.count : p.Q;
   const uint32_t xstep = p.x_on ? xchg::current_step(p.x) : 0u;
   const float* qbase = p.x_on ? p.x.q_all[p.x.rank] + (size_t)(xstep & 1u) * p.x.Q * 256 : p.q;
-  const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
-  const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
-  const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
   int S = 1;
   if (p.part_d && nrows > 0 && nrows < (int)gridDim.x) S = max(1, min((int)gridDim.x / nrows, p.G / EXACT_MIN_SLICE));
   const long long units = (long long)nrows * S;
+  if (units == 0) {        // the usual case (every row certified): leave before anything is loaded
+    if (p.x_on) xchg::signal_all(p.x, xchg::KIND_L, xstep, false);
+    return;
+  }
+  const Slice w0 = load_slice(p.fold + Fold::LAST_W, lane);
+  const Slice w1 = load_slice(p.fold + Fold::LAST_W + 256, lane);
+  const float b0 = p.fold[Fold::CONSTS + 5], b1 = p.fold[Fold::CONSTS + 6];
   float cd;
   int cidx;
   // the eight warps' sorted lists -> one sorted best-32 in warp 0

@@ -345,14 +345,15 @@ class SeamEngine:
         """All Q queries (once every rank's descriptors have landed here) against this rank's gallery shard; each
         query's top-k row is stored into the list buffer of the rank that owns the query."""
         gallery = self._fresh(gallery)
-        stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        # the diagnostic counters cost a fill, a memset and a copy node per step: only when asked for
+        stats = torch.zeros((4,), dtype=torch.int32, device=self.device) if return_stats else None
         nbytes = int(self._lib.seam_score_workspace_bytes(self._h, x.Q, gallery.G, x.k))
         ws = self._workspace("score", nbytes)
         self._check(self._lib.seam_sharded_score_topk(self._h, C.byref(x.struct), gallery.g.data_ptr(),
                                                       gallery.g16.data_ptr(), gallery.cg.data_ptr(),
                                                       gallery.gstat.data_ptr(), gallery.G, int(gallery.index_offset),
-                                                      stats.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
-        return stats if return_stats else None
+                                                      _ptr(stats), ws.data_ptr(), ws.numel(), self._stream()))
+        return stats
 
     def sharded_merge(self, x):
         """Merge the per-shard lists of the queries this rank owns and end the step.  Returns
@@ -422,7 +423,8 @@ class SeamEngine:
         sc = self._out(o[0], (Q, k), torch.float32, "score_topk scores")
         mg = self._out(o[1], (Q, k), torch.float32, "score_topk margins")
         ix = self._out(o[2], (Q, k), torch.int32, "score_topk idx")
-        stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        # the diagnostic counters cost a fill, a memset and a copy node per step: only when asked for
+        stats = torch.zeros((4,), dtype=torch.int32, device=self.device) if return_stats else None
         # The candidate lists take 12-96 KB per query row: very large evaluations are worked through in slabs of
         # queries that reuse one bounded workspace (results do not depend on the slab size)
         slab = Q
@@ -433,12 +435,12 @@ class SeamEngine:
             n = hi - lo
             nbytes = int(self._lib.seam_score_workspace_bytes(self._h, n, G, k))
             ws = self._workspace("score", nbytes)
-            st = stats if slab == Q else torch.zeros((4,), dtype=torch.int32, device=self.device)
+            st = stats if (slab == Q or stats is None) else torch.zeros((4,), dtype=torch.int32, device=self.device)
             self._check(self._lib.seam_score_topk(self._h, q[lo:hi].data_ptr() if n else 0, n, gallery.g.data_ptr(),
                                                   gallery.g16.data_ptr(), gallery.cg.data_ptr(),
                                                   gallery.gstat.data_ptr(), G, int(gallery.index_offset), k,
                                                   sc[lo:hi].data_ptr() if n else 0, mg[lo:hi].data_ptr() if n else 0,
-                                                  ix[lo:hi].data_ptr() if n else 0, st.data_ptr(),
+                                                  ix[lo:hi].data_ptr() if n else 0, _ptr(st),
                                                   ws.data_ptr(), ws.numel(), self._stream()))
             if st is not stats:
                 stats += st
@@ -460,12 +462,12 @@ class SeamEngine:
         sc = torch.empty((Q, k), dtype=torch.float32, device=self.device)
         mg = torch.empty((Q, k), dtype=torch.float32, device=self.device)
         ix = torch.empty((Q, k), dtype=torch.int32, device=self.device)
-        stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        stats = torch.zeros((4,), dtype=torch.int32, device=self.device) if return_stats else None
         ws = self._workspace("score", nbytes)
         self._check(self._lib.seam_search(self._h, seq.data_ptr() if Q else 0, _ptr(m8), _ptr(l32), Tmax, Q, seq.stride(0),
                                           seq.stride(1), q.data_ptr(), gallery.g.data_ptr(), gallery.g16.data_ptr(),
                                           gallery.cg.data_ptr(), gallery.gstat.data_ptr(), G, int(gallery.index_offset), k,
-                                          sc.data_ptr(), mg.data_ptr(), ix.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+                                          sc.data_ptr(), mg.data_ptr(), ix.data_ptr(), _ptr(stats), ws.data_ptr(),
                                           ws.numel(), self._stream()))
         return (q, sc, mg, ix, stats) if return_stats else (q, sc, mg, ix)
 
