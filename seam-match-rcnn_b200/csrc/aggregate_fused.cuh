@@ -22,6 +22,12 @@
 //
 // Results do not depend on how tracks are grouped into batches (a column of D depends on its own track
 // only; the accumulation order over k is fixed), nor on which slot a track lands in.
+//
+// A producer's iteration is a LATENCY CHAIN (2-3 producer warps per scheduler: shuffle rounds, named barriers,
+// shared-memory atomics, mbarrier polls and the hand-over of a copy to the copy engine all sit on one warp's
+// critical path), so the code below trades instructions for fewer dependent steps: reductions are folded into
+// loops that read the data anyway, warp maxima are one CREDUX, the softmax of a long track needs one barrier,
+// butterflies run over 32 totals, a loader warp issues the short-track kernel's copies.
 #pragma once
 #include <cstdint>
 #include <type_traits>
