@@ -44,7 +44,8 @@ if peer is not None:
         out3 = r.search_peer(seq, None, peer)
     # replay with DIFFERENT queries each time (the graph reads seq in place): parity halves and the step counter
     ok3 = True
-    for it in range(4):
+    NREP = int(os.environ.get("SEAM_CHECK_REPLAYS", "4"))
+    for it in range(NREP):
         seq[1:] = torch.randn(T, Q, 256, generator=torch.Generator().manual_seed(100 + it)).to(dev)
         dist.barrier()
         gph.replay()
@@ -52,9 +53,19 @@ if peer is not None:
         ref = pkg.search(eng, seq, None, gal, k) if rank == 0 else None
         if rank == 0:
             ok3 = ok3 and all(torch.equal(a, b) for a, b in zip(out3, ref))
+    # a burst of back-to-back replays without any host synchronisation in between (ranks drift up to a step apart:
+    # parity halves, step counter, multicast stores), then one more checked step
+    for _ in range(int(os.environ.get("SEAM_CHECK_BURST", "8"))):
+        gph.replay()
+    seq[1:] = torch.randn(T, Q, 256, generator=torch.Generator().manual_seed(999)).to(dev)
+    gph.replay()
+    torch.cuda.synchronize()
+    ref = pkg.search(eng, seq, None, gal, k) if rank == 0 else None
+    if rank == 0:
+        ok3 = ok3 and all(torch.equal(a, b) for a, b in zip(out3, ref))
     if rank == 0:
         same2 = torch.equal(ix2, ix1) and torch.equal(mg2, mg1) and torch.equal(sc2, sc1)
-        print(f"world={world}: in-kernel exchange vs single-GPU: eager identical={same2}, 4 graph replays with new queries "
+        print(f"world={world}: in-kernel exchange vs single-GPU: eager identical={same2}, {NREP} graph replays with new queries + a burst "
               f"identical={ok3}, steps done={peer.steps_done}, multicast={peer.multicast}, watchdog={eng.watchdog_records()}")
         ok = ok and same2 and ok3
 flag = torch.tensor([1 if ok else 0], device=dev)
