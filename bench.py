@@ -524,12 +524,13 @@ def run_ours(args):
     pairs_per_gpu = Q * Gs
     t_score, t_agg = kern["score"], kern["aggregate"]
     t_stage = sum(kern.get(n) or 0.0 for n in ("prep_queries", "score", "rescore", "exact"))
-    traffic = traffic_agg = None
+    traffic = traffic_agg = tensor_pipe_pct = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj.get("score_topk_kernel_dram_bytes_per_launch")
+        tensor_pipe_pct = tj.get("score_topk_kernel_tensor_pipe_active_pct")
         traffic_agg = tj.get("aggregate_fused_warp_kernel_dram_bytes_per_launch")
     roofline = {
         "kernel": "score_topk_kernel", "bound": "tensor",
@@ -541,6 +542,8 @@ def run_ours(args):
     }
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
     roofline["stage_frac"] = roofline["stage_achieved"] / roofline["peak"]
+    if tensor_pipe_pct is not None:      # ncu sm__pipe_tensor_subpipe_hmma_cycles_active (profiles/r2_final_ncu_score_topk_kernel.txt)
+        roofline["tensor_pipe_active_pct_ncu"] = tensor_pipe_pct
     if stage_graph_ms:
         roofline["stage_graph_ms"] = stage_graph_ms
         roofline["stage_graph_frac"] = pairs_per_gpu * FLOP_PER_PAIR / (stage_graph_ms * 1e-3) / 1e12 / roofline["peak"]
